@@ -1,0 +1,57 @@
+"""ctypes binding of libbftq.so (include/bftq.h).  Fails loudly when the library is missing:
+there is deliberately no Python or CPU fallback for any entry point."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbftq.so")
+
+
+class BftqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bftq error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("items", C.c_uint64), ("launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libbftq.so (built by __graft_entry__.build() / bftkv_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found - run `python -m bftkv_b200.build` "
+                          "(the CUDA extension is mandatory, there is no fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    sigs = {
+        "bftq_version": (C.c_int, []),
+        "bftq_last_error": (C.c_char_p, []),
+        "bftq_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "bftq_shutdown": (None, [vp]),
+        "bftq_device_sm_count": (C.c_int, [vp]),
+        "bftq_key_count": (C.c_int, [vp]),
+        "bftq_register_rsa_keys": (C.c_int, [vp, vp, vp, C.c_uint32, u32p]),
+        "bftq_rsa_verify_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp]),
+        "bftq_rsa_verify_batch_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]),
+        "bftq_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "bftq_measure_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise BftqError(rc, load().bftq_last_error().decode(errors="replace"))
