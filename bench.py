@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the bftkv signature-verify hot path on B200.
+
+Workload (BASELINE.json configs[1]): one batch of 65 536 RSA-2048 / SHA-256 PKCS#1 v1.5 signature
+verifies over 16 keys (1 % corrupted, 0.1 % unknown signer), synthetic.
+A "step" = one pass of the hot path over one such batch.  N GPUs = N independent shards
+(weak scaling, no collective on the data path; torch.distributed is used only for the barrier and
+the max-over-ranks time).
+
+  value     verifies/s, inputs already resident in HBM (device API, CUDA events on the launch stream)
+  e2e       verifies/s through the host C-ABI call with pinned HOST buffers: H2D + kernel + D2H per step
+  roofline  integer-ALU bound: 156 864 32x32->64 MACs per verify x verifies / kernel
+            time, against the IMAD.WIDE rate measured live on the same GPU (bftq_measure_int_peak)
+  cpu_baseline  the oracle's C port of the reference CPU path on the host cores (rank 0, N=1)
+
+`--impl reference` times the CPU restatement of the reference path (oracle/c; the Go reference
+itself cannot be built here: no Go toolchain, un-vendored x/crypto) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MACS_PER_VERIFY = 156864          # 19 Montgomery products x (2*64^2 + 64) word-MACs, SURVEY §8(d)
+BYTES_PER_VERIFY = 549            # n 256 + s 256 + digest 32 + key idx 4 + status 1, SURVEY §8(d)
+ITEMS = 65536
+NKEYS = 16
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        # the busiest samples are the ones under load: take the upper half
+        under = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": under[len(under) // 2] if under else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port(w, threads, reps):
+    from oracle import c_oracle
+    ns, es = [k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]]
+    c_oracle.rsa_verify_batch(ns, es, w["key_idx"][:512], w["sig"][:512], w["digest"][:512], threads=threads)   # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st = c_oracle.rsa_verify_batch(ns, es, w["key_idx"], w["sig"], w["digest"], threads=threads)
+    dt = time.perf_counter() - t0
+    return ITEMS * reps / dt, st
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from bftkv_b200 import workload
+    threads = os.cpu_count() or 1
+    w = workload.make_verify_batch(ITEMS, NKEYS)
+    for _ in range(args.warmup):
+        cpu_port(w, threads, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rate, st = cpu_port(w, threads, 1)
+    dt = time.perf_counter() - t0
+    assert (st == w["expect"]).all()
+    v = ITEMS * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "rsa2048_signature_verifies_per_sec", "value": v, "unit": "verifies/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+        "config": {"workload": "batch 65536 RSA-2048 PGP signature verifies (BASELINE configs[1]), 16 keys, SHA-256"},
+        "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": threads, "kind": "port",
+                         "sample": "the full 65536-item batch per step; oracle/c port of crypto/pgp -> rsa.VerifyPKCS1v15 "
+                                   "(the Go reference is unbuildable here: no Go toolchain, un-vendored x/crypto)"},
+        "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_gpu(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bftkv_b200 import Engine, workload
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = workload.make_verify_batch(ITEMS, NKEYS, seed=0xBF7C0002 + rank, corrupt_seed=0xBF7C0003 + rank,
+                                   threads=max(1, (os.cpu_count() or 8) // world))
+    eng = Engine(local_rank)
+    eng.register_rsa_keys([k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]])
+    int_peak = eng.measure_int_peak()
+
+    # ---- device-resident leg: COPIES distinct input sets (> L2) rotated between steps ----------
+    copies = args.copies
+    d_idx = [torch.from_numpy(w["key_idx"].astype(np.int32)).to(dev) for _ in range(copies)]
+    d_sig = [torch.from_numpy(w["sig"]).to(dev) for _ in range(copies)]
+    d_dig = [torch.from_numpy(w["digest"]).to(dev) for _ in range(copies)]
+    d_st = [torch.empty(ITEMS, dtype=torch.uint8, device=dev) for _ in range(copies)]
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i):
+        c = i % copies
+        eng.rsa_verify_batch_dev(d_idx[c], d_sig[c], d_dig[c], ITEMS, d_st[c], stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.stats()["launches"]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step(i)
+        evs[i + 1].record(stream)
+    stream.synchronize()
+    barrier()
+    dev_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    gpu_launches = eng.stats()["launches"] - launches0
+    for c in range(min(copies, args.steps)):
+        assert np.array_equal(d_st[c].cpu().numpy(), w["expect"]), "device-resident results differ from expectation"
+
+    # ---- end-to-end leg: pinned host buffers through the host C-ABI call ------------------------
+    h_idx = torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory()
+    h_sig = torch.from_numpy(w["sig"]).pin_memory()
+    h_dig = torch.from_numpy(w["digest"]).pin_memory()
+    h_st = torch.empty(ITEMS, dtype=torch.uint8).pin_memory()
+    for _ in range(args.warmup):
+        eng.rsa_verify_batch(h_idx, h_sig, h_dig, out=h_st)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.rsa_verify_batch(h_idx, h_sig, h_dig, out=h_st)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(h_st.numpy(), w["expect"]), "end-to-end results differ from expectation"
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_items = ITEMS * world * args.steps
+    value = total_items / (dev_ms * 1e-3)
+    e2e_v = total_items / (e2e_ms * 1e-3)
+    k_avg_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = MACS_PER_VERIFY * ITEMS / (k_avg_ms * 1e-3)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "measured"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+    hbm_ach = BYTES_PER_VERIFY * ITEMS / (k_avg_ms * 1e-3) / 1e9
+    out = {
+        "metric": "rsa2048_signature_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 digits / u64 accumulators (integer)", "data": "synthetic",
+        "config": {"workload": "batch 65536 RSA-2048 PGP signature verifies (BASELINE configs[1]), 16 keys, e=65537, SHA-256, "
+                               "1% corrupted + 0.1% unknown signer",
+                   "per_gpu_batch": ITEMS, "l2": "inputs rotated over %d distinct device copies (%d MB > 126 MB L2)"
+                   % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4"))},
+        "gpu_launches": int(gpu_launches),
+        "e2e": {"value": e2e_v, "unit": "verifies/s", "h2d_bytes_per_step": ITEMS * (256 + 32 + 4), "d2h_bytes_per_step": ITEMS,
+                "api": "bftq_rsa_verify_batch (host C ABI, pinned host buffers)", "ms_per_step": e2e_ms / args.steps},
+        "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE)",
+                     "frac": achieved / int_peak, "traffic": None,
+                     "peak_source": "measured live: dependency-free mad.wide.u32 micro-benchmark (bftq_measure_int_peak)",
+                     "kernel": "rsa_verify_kernel", "kernel_ms_avg": k_avg_ms, "kernel_ms_min": kernel_ms[0],
+                     "algorithmic_macs_per_verify": MACS_PER_VERIFY,
+                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "algorithmic_bytes_per_verify": BYTES_PER_VERIFY}},
+        "clocks": clocks,
+    }
+    if world == 1:
+        threads = os.cpu_count() or 1
+        reps = 8
+        rate, st = cpu_port(w, threads, reps)
+        assert (st == w["expect"]).all()
+        out["cpu_baseline"] = {"value": rate, "unit": "verifies/s", "cores": threads, "kind": "port",
+                               "sample": "%d passes over the same 65536-item batch (%d verifies), oracle/c port on %d host threads"
+                               % (reps, reps * ITEMS, threads)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--copies", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

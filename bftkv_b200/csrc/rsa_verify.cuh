@@ -266,7 +266,7 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
       }
       uint32_t m1[W];
 #pragma unroll
-      for (int j = 0; j < W; j++) m1[j] = (e & 1u) ? xs[j] : ((r == 0 && j == 0) ? 1u : 0u);
+      for (int j = 0; j < W; j++) m1[j] = ((e & 1u) && nb >= 2) ? xs[j] : ((r == 0 && j == 0) ? 1u : 0u);   // e == 1: bit 0 is the top bit, already in y
       mont_mul<T, W>(t, y, m1, nd, n0inv, r, gbase);
 #pragma unroll
       for (int j = 0; j < W; j++) y[j] = t[j];

@@ -1,0 +1,86 @@
+"""Synthetic signed-packet workloads for tests and bench.py.
+
+Not on the hot path: this only MAKES inputs (RSA signing on the host with OpenSSL via
+`cryptography`, packet bytes per packet/packet.go:35-60) — verification is never done here."""
+import hashlib
+import json
+import os
+import struct
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS_JSON = os.path.join(_HERE, "..", "tests", "golden", "rsa_keys_bf7c0001.json")
+SHA256_PREFIX = bytes.fromhex("3031300d060960864801650304020105000420")
+
+
+def load_keys(k: int):
+    """First k deterministic RSA-2048 test keys: list of dicts with p, q, n, d, e (ints)."""
+    data = json.load(open(KEYS_JSON))
+    out = []
+    for kd in data["keys"][:k]:
+        p, q = int(kd["p"], 16), int(kd["q"], 16)
+        n, e = p * q, data["e"]
+        d = pow(e, -1, (p - 1) * (q - 1))
+        out.append({"p": p, "q": q, "n": n, "d": d, "e": e})
+    assert len(out) == k, "not enough fixture keys"
+    return out
+
+
+def _private_key(k):
+    from cryptography.hazmat.primitives.asymmetric.rsa import RSAPrivateNumbers, RSAPublicNumbers
+    p, q, d = k["p"], k["q"], k["d"]
+    return RSAPrivateNumbers(p, q, d, d % (p - 1), d % (q - 1), pow(q, -1, p),
+                             RSAPublicNumbers(k["e"], k["n"])).private_key()
+
+
+def tbs_packet(x: bytes, v: bytes, t: int) -> bytes:
+    """packet.Serialize(x, v, t) == the TBS bytes (packet/packet.go:35-60,156-168)."""
+    return struct.pack(">Q", len(x)) + x + struct.pack(">Q", len(v)) + v + struct.pack(">Q", t)
+
+
+def make_verify_batch(n_items: int, n_keys: int = 16, seed: int = 0xBF7C0002, corrupt_rate: float = 0.01,
+                      unknown_rate: float = 0.001, corrupt_seed: int = 0xBF7C0003, threads: int = 0):
+    """Config 2: N tuples over K keys.  message_i = packet.Serialize(x_i(16 B), v_i(32 B), t=i);
+    digest_i = SHA-256(message_i) (the raw PKCS#1 case; the OpenPGP v4 digest adds a suffix, see
+    pgp host layer); signatures by OpenSSL; a seeded fraction corrupted / given an unknown key.
+    Returns dict(keys, key_idx u32[N], sig u8[N,256], digest u8[N,32], expect u8[N])."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding
+    from cryptography.hazmat.primitives.asymmetric.utils import Prehashed
+    keys = load_keys(n_keys)
+    privs = [_private_key(k) for k in keys]
+    rng = np.random.default_rng(seed)
+    key_idx = rng.integers(0, n_keys, n_items).astype(np.uint32)
+    xv = rng.integers(0, 256, (n_items, 48), dtype=np.uint8)
+    digest = np.empty((n_items, 32), np.uint8)
+    sig = np.empty((n_items, 256), np.uint8)
+    threads = threads or min(32, os.cpu_count() or 1)
+
+    def work(lo_hi):
+        lo, hi = lo_hi
+        pad, ph = padding.PKCS1v15(), Prehashed(hashes.SHA256())
+        for i in range(lo, hi):
+            m = tbs_packet(xv[i, :16].tobytes(), xv[i, 16:].tobytes(), i)
+            d = hashlib.sha256(m).digest()
+            digest[i] = np.frombuffer(d, np.uint8)
+            sig[i] = np.frombuffer(privs[key_idx[i]].sign(d, pad, ph), np.uint8)
+
+    step = max(1, (n_items + threads * 4 - 1) // (threads * 4))
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, [(lo, min(n_items, lo + step)) for lo in range(0, n_items, step)]))
+    expect = np.zeros(n_items, np.uint8)
+    crng = np.random.default_rng(corrupt_seed)
+    bad = crng.random(n_items) < corrupt_rate
+    for i in np.nonzero(bad)[0]:
+        sig[i, crng.integers(0, 256)] ^= np.uint8(1 << crng.integers(0, 8))
+        expect[i] = 1
+    unk = crng.random(n_items) < unknown_rate
+    key_idx[unk] = n_keys + 7
+    expect[unk] = 4
+    return {"keys": keys, "key_idx": key_idx, "sig": sig, "digest": digest, "expect": expect}
+
+
+def em_for_digest(digest: bytes) -> int:
+    return int.from_bytes(b"\x00\x01" + b"\xff" * 202 + b"\x00" + SHA256_PREFIX + digest, "big")

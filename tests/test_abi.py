@@ -1,0 +1,46 @@
+"""CPU suite: libbftq.so loads and exports every symbol include/bftq.h declares.  No compute."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(built):
+    hdr = open(os.path.join(ROOT, "include", "bftq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bftq_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(os.path.join(ROOT, "bftkv_b200", "libbftq.so"))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.bftq_version() == int(re.search(r"#define BFTQ_VERSION (\d+)", hdr).group(1))
+
+
+def test_binding_loads_and_fails_loudly_without_gpu(built):
+    import torch
+    from bftkv_b200 import _lib, Engine
+    _lib.load()
+    if not torch.cuda.is_available():
+        try:
+            Engine(0)
+        except _lib.BftqError as e:
+            assert e.code == -1          # BFTQ_ERR_NO_DEVICE: no CPU fallback exists
+        else:
+            raise AssertionError("Engine() must fail without a CUDA device")
+
+
+def test_sass_is_carry_free_imad_wide(built):
+    """The RSA kernel's inner loop must be plain IMAD.WIDE.U32 (no .X carry chain): that is the
+    design decision profiles/int_pipe_ubench_r01.json justifies."""
+    import subprocess
+    so = os.path.join(ROOT, "bftkv_b200", "libbftq.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    blocks = sass.split("Function :")
+    rsa = [b for b in blocks if "rsa_verify_kernel" in b.split("\n")[0]]
+    assert rsa
+    for b in rsa:
+        wide = len(re.findall(r"IMAD\.WIDE\.U32 ", b))
+        widex = len(re.findall(r"IMAD\.WIDE\.U32\.X", b))
+        assert wide > 100 and widex == 0, (wide, widex)
