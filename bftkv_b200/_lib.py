@@ -41,6 +41,26 @@ def load():
         "bftq_register_rsa_keys": (C.c_int, [vp, vp, vp, C.c_uint32, u32p]),
         "bftq_rsa_verify_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp]),
         "bftq_rsa_verify_batch_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]),
+        "bftq_quorum_create": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(vp)]),
+        "bftq_quorum_destroy": (None, [vp, vp]),
+        "bftq_tally_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint64, vp]),
+        "bftq_read_tally_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp]),
+        "bftq_verify_tally_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp, vp]),
+        "bftq_verify_tally_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_uint64,
+                                                  C.c_uint32, vp, vp, vp, vp]),
+        "bftq_lagrange_combine_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, vp]),
+        "bftq_pgp_digest_batch": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint64, vp]),
+        "bftq_keyring_create": (C.c_int, [vp, C.POINTER(vp)]),
+        "bftq_keyring_destroy": (None, [vp]),
+        "bftq_keyring_add": (C.c_int, [vp, vp, C.c_uint64, C.c_int, u32p]),
+        "bftq_keyring_remove": (C.c_int, [vp, vp, C.c_uint32]),
+        "bftq_keyring_ids": (C.c_int, [vp, vp, C.c_uint32, u32p]),
+        "bftq_keyring_certifiers": (C.c_int, [vp, C.c_uint64, vp, C.c_uint32, u32p]),
+        "bftq_signature_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint64, vp]),
+        "bftq_signature_verify_with_cert_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp]),
+        "bftq_signature_signers": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u32p]),
+        "bftq_collective_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint64, vp]),
+        "bftq_collective_combine_sufficient": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_int32)]),
         "bftq_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "bftq_measure_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
     }

@@ -1,0 +1,193 @@
+"""Host-side mirror of the reference's operator interfaces for the hot path, over libbftq.so.
+
+Names and argument meaning follow the reference (so tests read like the reference's own):
+  crypto.Keyring              crypto/crypto.go:35-41      -> Keyring.register / remove / get_keyring
+  crypto.Signature            crypto/crypto.go:50-58      -> Signature.verify / verify_with_certificate / signers
+  crypto.CollectiveSignature  crypto/crypto.go:66-71      -> CollectiveSignature.verify / combine / signers
+  quorum.Quorum               quorum/quorum.go:18-25      -> Quorum.is_quorum / is_threshold / is_sufficient / reject
+Errors are the reference's sentinels (crypto/crypto.go:13-33): every verification failure is
+ErrInvalidSignature, a collective signature without enough valid signers is
+ErrInsufficientNumberOfSignatures.  Each call is a batch of one; the *_batch variants are what a
+batching aggregator (the Go shim's coalescer) feeds.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine, QC, TALLY_IS_QUORUM, TALLY_IS_SUFFICIENT, TALLY_IS_THRESHOLD, TALLY_REJECT
+
+ErrInvalidSignature = "crypto: invalid signature"
+ErrInsufficientNumberOfSignatures = "crypto: insufficient number of signatures"
+_ERR = {0: None, -6: ErrInvalidSignature, -7: ErrInsufficientNumberOfSignatures}
+
+
+def _blob(items: Sequence[bytes]):
+    off = np.zeros(len(items) + 1, np.uint64)
+    off[1:] = np.cumsum([len(b) for b in items])
+    blob = np.frombuffer(b"".join(items) or b"\0", np.uint8).copy()
+    return blob, off
+
+
+class QCIds(C.Structure):
+    _fields_ = [("f", C.c_int32), ("min", C.c_int32), ("threshold", C.c_int32), ("suff", C.c_int32),
+                ("member_off", C.c_uint32), ("member_cnt", C.c_uint32)]
+
+
+class Quorum:
+    """A wotqs quorum (quorum/wotqs/wotqs.go:24-26): list of (f, min, threshold, suff, [node ids])."""
+
+    def __init__(self, engine: Engine, qcs: Sequence[Tuple[int, int, int, int, Sequence[int]]]):
+        self.engine, self.qcs = engine, [(f, mn, th, sf, list(m)) for f, mn, th, sf, m in qcs]
+        ids = sorted({i for q in self.qcs for i in q[4]})
+        self._dense = {nid: k for k, nid in enumerate(ids)}
+        self._h = engine.quorum_create([(f, mn, th, sf, [self._dense[i] for i in m]) for f, mn, th, sf, m in self.qcs])
+
+    def _c_desc(self):
+        arr = (QCIds * max(1, len(self.qcs)))()
+        members, off = [], 0
+        for i, (f, mn, th, sf, m) in enumerate(self.qcs):
+            arr[i] = QCIds(f, mn, th, sf, off, len(m))
+            members += m
+            off += len(m)
+        return arr, np.asarray(members if members else [0], np.uint64), len(members)
+
+    def _bits(self, nodes: Sequence[int], failed=False) -> int:
+        unknown = len(self._dense)
+        idx = np.asarray([self._dense.get(n, unknown) for n in nodes] or [0], np.uint32)
+        st = np.full(len(idx), 1 if failed else 0, np.uint8)
+        off = np.asarray([0, len(nodes)], np.uint32)
+        return int(self.engine.tally_batch(self._h, off, idx, st)[0])
+
+    def nodes(self) -> List[int]:
+        return [i for q in self.qcs for i in q[4]]
+
+    def is_quorum(self, nodes) -> bool:
+        return bool(self._bits(nodes) & TALLY_IS_QUORUM)
+
+    def is_threshold(self, nodes) -> bool:
+        return bool(self._bits(nodes) & TALLY_IS_THRESHOLD)
+
+    def is_sufficient(self, nodes) -> bool:
+        return bool(self._bits(nodes) & TALLY_IS_SUFFICIENT)
+
+    def reject(self, nodes) -> bool:
+        return bool(self._bits(nodes, failed=True) & TALLY_REJECT)
+
+    def get_threshold(self) -> int:
+        return sum(q[2] for q in self.qcs)
+
+
+class Keyring:
+    """crypto/pgp PGPKeyring (crypto_pgp.go:115-223) over bftq_keyring."""
+
+    def __init__(self, engine: Engine):
+        self.engine, self._lib = engine, _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.bftq_keyring_create(engine._h, C.byref(h)))
+        self._h = h
+
+    def register(self, key_blocks: bytes, priv: bool = False) -> int:
+        buf = np.frombuffer(key_blocks or b"\0", np.uint8).copy()
+        n = C.c_uint32()
+        _lib.check(self._lib.bftq_keyring_add(self._h, C.c_void_p(buf.ctypes.data), len(key_blocks), int(priv), C.byref(n)))
+        return n.value
+
+    def remove(self, ids: Sequence[int]):
+        a = np.asarray(list(ids) or [0], np.uint64)
+        _lib.check(self._lib.bftq_keyring_remove(self._h, C.c_void_p(a.ctypes.data), len(ids)))
+
+    def get_keyring(self) -> List[int]:
+        n = C.c_uint32()
+        _lib.check(self._lib.bftq_keyring_ids(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), np.uint64)
+        _lib.check(self._lib.bftq_keyring_ids(self._h, C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return [int(x) for x in out[:n.value]]
+
+    def certifiers(self, key_id: int) -> List[int]:
+        n = C.c_uint32()
+        _lib.check(self._lib.bftq_keyring_certifiers(self._h, key_id, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), np.uint64)
+        _lib.check(self._lib.bftq_keyring_certifiers(self._h, key_id, C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return [int(x) for x in out[:n.value]]
+
+    def close(self):
+        if self._h:
+            self._lib.bftq_keyring_destroy(self._h)
+            self._h = None
+
+
+class Signature:
+    """crypto.Signature's verification half (crypto_pgp.go:319-344,373-390)."""
+
+    def __init__(self, keyring: Keyring):
+        self.keyring, self._lib = keyring, _lib.load()
+
+    def verify_batch(self, tbs: Sequence[bytes], sig_data: Sequence[bytes], certs: Optional[Sequence[bytes]] = None):
+        n = len(tbs)
+        tb, to = _blob(tbs)
+        sb, so = _blob(sig_data)
+        err = np.zeros(max(n, 1), np.int32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        if certs is None:
+            _lib.check(self._lib.bftq_signature_verify_batch(self.keyring._h, p(tb), p(to), p(sb), p(so), n, p(err)))
+        else:
+            cb, co = _blob(certs)
+            _lib.check(self._lib.bftq_signature_verify_with_cert_batch(self.keyring._h, p(tb), p(to), p(sb), p(so), p(cb), p(co), n, p(err)))
+        return [_ERR[int(e)] for e in err[:n]]
+
+    def verify(self, tbs: bytes, sig_data: bytes) -> Optional[str]:
+        return self.verify_batch([tbs], [sig_data])[0]
+
+    def verify_with_certificate(self, tbs: bytes, sig_data: bytes, cert: bytes) -> Optional[str]:
+        return self.verify_batch([tbs], [sig_data], [cert])[0]
+
+    def signers(self, sig_data: bytes) -> List[int]:
+        buf = np.frombuffer(sig_data or b"\0", np.uint8).copy()
+        out = np.zeros(256, np.uint64)
+        n = C.c_uint32()
+        _lib.check(self._lib.bftq_signature_signers(self.keyring._h, C.c_void_p(buf.ctypes.data), len(sig_data),
+                                                    C.c_void_p(out.ctypes.data), 256, C.byref(n)))
+        return [int(x) for x in out[:n.value]]
+
+
+class CollectiveSignature:
+    """crypto.CollectiveSignature (crypto_pgp.go:485-515)."""
+
+    def __init__(self, signature: Signature):
+        self.signature, self._lib = signature, _lib.load()
+
+    def verify_batch(self, tbs: Sequence[bytes], ss_data: Sequence[bytes], q: Quorum):
+        n = len(tbs)
+        tb, to = _blob(tbs)
+        sb, so = _blob(ss_data)
+        arr, members, nm = q._c_desc()
+        err = np.zeros(max(n, 1), np.int32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(self._lib.bftq_collective_verify_batch(self.signature.keyring._h, C.cast(arr, C.c_void_p), len(q.qcs), p(members), nm,
+                                                          p(tb), p(to), p(sb), p(so), n, p(err)))
+        return [_ERR[int(e)] for e in err[:n]]
+
+    def verify(self, tbs: bytes, ss_data: bytes, q: Quorum):
+        """Returns (error, completed) — the reference sets ss.Completed = true on success."""
+        e = self.verify_batch([tbs], [ss_data], q)[0]
+        return e, e is None
+
+    def combine(self, ss_type: int, ss_data: bytes, s_type: int, s_data: bytes, q: Quorum):
+        """Returns (sufficient, new_type, new_data) — crypto_pgp.go:506-515."""
+        if ss_type == 0:
+            ss_type = s_type
+        elif ss_type != s_type:
+            return False, ss_type, ss_data
+        ss_data = (ss_data or b"") + (s_data or b"")
+        buf = np.frombuffer(ss_data or b"\0", np.uint8).copy()
+        arr, members, nm = q._c_desc()
+        out = C.c_int32()
+        _lib.check(self._lib.bftq_collective_combine_sufficient(self.signature.keyring._h, C.cast(arr, C.c_void_p), len(q.qcs),
+                                                                C.c_void_p(members.ctypes.data), nm, C.c_void_p(buf.ctypes.data),
+                                                                len(ss_data), C.byref(out)))
+        return bool(out.value), ss_type, ss_data
+
+    def signers(self, ss_data: bytes) -> List[int]:
+        return self.signature.signers(ss_data)

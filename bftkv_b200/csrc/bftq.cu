@@ -3,11 +3,16 @@
 // pinned staging.  No CPU verification path exists here on purpose.
 #include "../../include/bftq.h"
 #include "rsa_verify.cuh"
+#include "tally.cuh"
+#include "lagrange.cuh"
+#include "pgp_digest.cuh"
+#include "pgp_host.hpp"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -92,16 +97,12 @@ struct bftq_engine {
   size_t d_keys_cap = 0;
   std::vector<StagingSlot*> slots;
   bftq_stats_t stats{};
+  std::map<std::string, uint32_t> key_lookup;   // (modulus bytes || e) -> key table index
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
 
 namespace {
-
-struct SlotLease {
-  bftq_engine* e; StagingSlot* s;
-  ~SlotLease() { std::lock_guard<std::mutex> g(e->mu); s->busy = false; }
-};
 
 int acquire_slot(bftq_engine* e, size_t h_bytes, size_t d_bytes, StagingSlot** out) {
   StagingSlot* s = nullptr;
@@ -129,9 +130,78 @@ int acquire_slot(bftq_engine* e, size_t h_bytes, size_t d_bytes, StagingSlot** o
   return BFTQ_OK;
 }
 
+// A call's staging plan: device buffers carved out of one slot, inputs uploaded in one go,
+// outputs downloaded in one go.  Pinned caller memory is DMA'd directly, pageable memory is
+// bounced through the slot's pinned mirror.
+class Arena {
+ public:
+  explicit Arena(bftq_engine* e) : e_(e) {}
+  ~Arena() { if (s_) { std::lock_guard<std::mutex> g(e_->mu); s_->busy = false; } }
+  // count = elements reserved on the device, copy = elements actually copied (defaults to count)
+  template <typename T> void in(T** dptr, const T* host, size_t count, size_t copy = (size_t)-1) {
+    add((void**)dptr, (void*)host, count * sizeof(T), (copy == (size_t)-1 ? count : copy) * sizeof(T), true);
+  }
+  template <typename T> void out(T** dptr, T* host, size_t count, size_t copy = (size_t)-1) {
+    add((void**)dptr, (void*)host, count * sizeof(T), (copy == (size_t)-1 ? count : copy) * sizeof(T), false);
+  }
+  cudaStream_t stream() const { return s_->stream; }
+  int upload() {
+    int rc = acquire_slot(e_, total_, total_, &s_);
+    if (rc) return rc;
+    uint64_t h2d = 0;
+    for (auto& b : bufs_) {
+      *b.dptr = s_->d_buf + b.off;
+      if (!b.is_in || b.copy == 0) continue;
+      const void* from = b.host;
+      if (!is_pinned(b.host)) { memcpy(s_->h_pinned + b.off, b.host, b.copy); from = s_->h_pinned + b.off; }
+      CU(cudaMemcpyAsync(s_->d_buf + b.off, from, b.copy, cudaMemcpyHostToDevice, s_->stream));
+      h2d += b.copy;
+    }
+    std::lock_guard<std::mutex> g(e_->mu);
+    e_->stats.h2d_bytes += h2d;
+    return BFTQ_OK;
+  }
+  int download() {
+    uint64_t d2h = 0;
+    std::vector<const Buf*> bounce;
+    for (auto& b : bufs_) {
+      if (b.is_in || b.copy == 0) continue;
+      if (is_pinned(b.host)) {
+        CU(cudaMemcpyAsync(b.host, s_->d_buf + b.off, b.copy, cudaMemcpyDeviceToHost, s_->stream));
+      } else {
+        CU(cudaMemcpyAsync(s_->h_pinned + b.off, s_->d_buf + b.off, b.copy, cudaMemcpyDeviceToHost, s_->stream));
+        bounce.push_back(&b);
+      }
+      d2h += b.copy;
+    }
+    CU(cudaStreamSynchronize(s_->stream));
+    for (auto* b : bounce) memcpy(b->host, s_->h_pinned + b->off, b->copy);
+    std::lock_guard<std::mutex> g(e_->mu);
+    e_->stats.d2h_bytes += d2h;
+    return BFTQ_OK;
+  }
+
+ private:
+  struct Buf { void** dptr; void* host; size_t off, bytes, copy; bool is_in; };
+  void add(void** dptr, void* host, size_t bytes, size_t copy, bool is_in) {
+    bufs_.push_back({dptr, host, total_, bytes, copy, is_in});
+    total_ += (bytes + 255) & ~(size_t)255;
+  }
+  static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+  }
+  bftq_engine* e_;
+  StagingSlot* s_ = nullptr;
+  std::vector<Buf> bufs_;
+  size_t total_ = 0;
+};
+
 template <int T, int W, int BLOCK>
 int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
-               uint32_t hash_alg, uint64_t n_items, uint32_t flags, uint8_t* d_status, cudaStream_t st) {
+               uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st) {
   auto kern = bftq::rsa_verify_kernel<T, W, BLOCK>;
   static thread_local int occ_cache = 0;
   int occ = occ_cache;
@@ -145,34 +215,41 @@ int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, 
   uint64_t grid = std::min<uint64_t>(need, (uint64_t)e->sm_count * occ);
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, BLOCK, 0, st>>>(e->d_keys, (uint32_t)e->h_keys.size(), d_key_idx, d_sig, d_digest, hash_alg,
-                                         n_items, flags, d_status);
+                                         n_items, flags, d_pre, d_status);
   CU(cudaGetLastError());
   return BFTQ_OK;
 }
 
 int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
-                   uint32_t hash_alg, uint64_t n_items, uint32_t flags, uint8_t* d_status, cudaStream_t st) {
+                   uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> g(e->mu);
     e->stats.launches += 1;
     e->stats.items += n_items;
   }
   switch (e->rsa_t) {
-    case 8: return launch_rsa<8, 10, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_status, st);
-    default: return launch_rsa<4, 19, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_status, st);
+    case 8: return launch_rsa<8, 10, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    default: return launch_rsa<4, 19, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
   }
 }
 
 // ---- integer-pipe peak micro-benchmark ---------------------------------------------------------
+// 16 independent accumulators per thread; the multiplicand changes every iteration (rotated through
+// the accumulators' own low words) so ptxas cannot strength-reduce the products into additions —
+// an earlier version with loop-invariant multiplicands was silently turned into IADD3 pairs and
+// reported the ALU-pipe rate instead (profiles/int_pipe_ubench_r01.json, "imad_wide_*" rows).
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, uint32_t seed, int iters) {
   unsigned long long acc[16];
-  uint32_t a[4];
-  const uint32_t b = (seed | 1u) + 2u * threadIdx.x;
-  for (int i = 0; i < 4; i++) a[i] = (seed ^ 0x9e3779b9u) * (i + 1) + threadIdx.x;
-  for (int i = 0; i < 16; i++) acc[i] = threadIdx.x + i * seed;
+  uint32_t a[16];
+  for (int i = 0; i < 16; i++) {
+    acc[i] = (unsigned long long)(threadIdx.x + 1) * (i + seed);
+    a[i] = (seed ^ 0x9e3779b9u) * (2 * i + 1) + threadIdx.x;
+  }
+#pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    const uint32_t b = __shfl_xor_sync(0xffffffffu, (uint32_t)acc[0], 1) | 1u;   // opaque, changes every iteration
 #pragma unroll
-    for (int i = 0; i < 16; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i & 3]), "r"(b));
+    for (int i = 0; i < 16; i++) acc[i] += (unsigned long long)a[i] * b;     // IMAD.WIDE.U32 R, a, b, R
   }
   unsigned long long s = 0;
   for (int i = 0; i < 16; i++) s ^= acc[i];
@@ -292,7 +369,7 @@ int bftq_rsa_verify_batch_dev(bftq_engine* e, const uint32_t* d_key_idx, const u
   if (n_items == 0) return BFTQ_OK;
   if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   CU(cudaSetDevice(e->device));
-  return launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_status, (cudaStream_t)cuda_stream);
+  return launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, nullptr, d_status, (cudaStream_t)cuda_stream);
 }
 
 int bftq_rsa_verify_batch(bftq_engine* e, const uint32_t* key_idx, const uint8_t* sig_be, const uint8_t* digest,
@@ -302,48 +379,703 @@ int bftq_rsa_verify_batch(bftq_engine* e, const uint32_t* key_idx, const uint8_t
   if (dlen == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_items == 0) return BFTQ_OK;
   if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
-  // device layout of one staging buffer: [sig | digest | key_idx | status]
-  const size_t sig_b = (size_t)n_items * 256, dig_b = (size_t)n_items * dlen, idx_b = (size_t)n_items * 4;
-  const size_t off_dig = sig_b, off_idx = (off_dig + dig_b + 15) & ~(size_t)15, off_st = off_idx + idx_b;
-  const size_t total = off_st + n_items;
-  StagingSlot* s = nullptr;
-  int rc = acquire_slot(e, total, total, &s);
+  Arena a(e);
+  uint8_t *d_sig, *d_dig, *d_st; uint32_t* d_idx;
+  a.in(&d_sig, sig_be, (size_t)n_items * 256);
+  a.in(&d_dig, digest, (size_t)n_items * dlen);
+  a.in(&d_idx, key_idx, (size_t)n_items);
+  a.out(&d_st, out_status, (size_t)n_items);
+  int rc = a.upload();
   if (rc) return rc;
-  SlotLease lease{e, s};
-  // Pinned caller buffers go straight over PCIe; pageable ones are staged through pinned memory.
-  auto h2d = [&](size_t off, const void* src, size_t bytes) -> int {
-    cudaPointerAttributes at;
-    bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    const void* from = src;
-    if (!pinned) { memcpy(s->h_pinned + off, src, bytes); from = s->h_pinned + off; }
-    CU(cudaMemcpyAsync(s->d_buf + off, from, bytes, cudaMemcpyHostToDevice, s->stream));
-    return BFTQ_OK;
-  };
-  if ((rc = h2d(0, sig_be, sig_b))) return rc;
-  if ((rc = h2d(off_dig, digest, dig_b))) return rc;
-  if ((rc = h2d(off_idx, key_idx, idx_b))) return rc;
-  rc = launch_rsa_any(e, (const uint32_t*)(s->d_buf + off_idx), s->d_buf, s->d_buf + off_dig, hash_alg, n_items, flags,
-                      s->d_buf + off_st, s->stream);
+  rc = launch_rsa_any(e, d_idx, d_sig, d_dig, hash_alg, n_items, flags, nullptr, d_st, a.stream());
   if (rc) return rc;
-  {
-    cudaPointerAttributes at;
-    bool pinned = cudaPointerGetAttributes(&at, out_status) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned) {
-      CU(cudaMemcpyAsync(out_status, s->d_buf + off_st, n_items, cudaMemcpyDeviceToHost, s->stream));
-      CU(cudaStreamSynchronize(s->stream));
-    } else {
-      CU(cudaMemcpyAsync(s->h_pinned + off_st, s->d_buf + off_st, n_items, cudaMemcpyDeviceToHost, s->stream));
-      CU(cudaStreamSynchronize(s->stream));
-      memcpy(out_status, s->h_pinned + off_st, n_items);
+  return a.download();
+}
+
+// ---- K2 ---------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct bftq_quorum {
+  bftq::QuorumDev dev;
+  uint32_t* d_bits = nullptr;
+};
+
+namespace {
+int launch_tally(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_off, const uint32_t* d_idx, const uint8_t* d_status,
+                 const uint64_t* d_ts, const uint32_t* d_val, uint64_t n_ops, uint32_t* d_winner, uint8_t* d_bits, cudaStream_t st) {
+  const int block = 256, wpb = block / 32;
+  uint64_t grid = std::min<uint64_t>((n_ops + wpb - 1) / wpb, (uint64_t)e->sm_count * 8);
+  if (grid < 1) grid = 1;
+  if (d_ts && d_val)
+    bftq::read_tally_kernel<<<(unsigned)grid, block, 0, st>>>(q->dev, d_off, d_idx, d_status, d_ts, d_val, n_ops, d_winner, d_bits);
+  else
+    bftq::tally_kernel<<<(unsigned)grid, block, 0, st>>>(q->dev, d_off, d_idx, d_status, n_ops, d_bits);
+  CU(cudaGetLastError());
+  std::lock_guard<std::mutex> g(e->mu);
+  e->stats.launches += 1;
+  return BFTQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bftq_quorum_create(bftq_engine* e, const bftq_qc_t* qcs, uint32_t n_qc, const uint32_t* member_key_idx,
+                       uint32_t n_members, bftq_quorum** out) {
+  if (!e || !out || (n_qc && !qcs) || (n_members && !member_key_idx)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_qc > (uint32_t)bftq::kMaxQc) return fail(BFTQ_ERR_INVALID_ARG, "too many quorum cliques");
+  uint32_t maxk = 0;
+  for (uint32_t c = 0; c < n_qc; c++) {
+    if ((uint64_t)qcs[c].member_off + qcs[c].member_cnt > n_members) return fail(BFTQ_ERR_INVALID_ARG, "clique members out of range");
+    for (uint32_t m = 0; m < qcs[c].member_cnt; m++) maxk = std::max(maxk, member_key_idx[qcs[c].member_off + m]);
+  }
+  if (maxk > (1u << 20)) return fail(BFTQ_ERR_INVALID_ARG, "member key index too large");
+  auto* q = new bftq_quorum();
+  memset(&q->dev, 0, sizeof(q->dev));
+  q->dev.nqc = (int32_t)n_qc;
+  q->dev.nkeys_words = maxk / 32 + 1;
+  std::vector<uint32_t> bits((size_t)std::max<uint32_t>(n_qc, 1) * q->dev.nkeys_words, 0u);
+  for (uint32_t c = 0; c < n_qc; c++) {
+    q->dev.f[c] = qcs[c].f; q->dev.min[c] = qcs[c].min; q->dev.threshold[c] = qcs[c].threshold; q->dev.suff[c] = qcs[c].suff;
+    for (uint32_t m = 0; m < qcs[c].member_cnt; m++) {
+      const uint32_t k = member_key_idx[qcs[c].member_off + m];
+      bits[(size_t)c * q->dev.nkeys_words + (k >> 5)] |= 1u << (k & 31);
     }
   }
+  cudaSetDevice(e->device);
+  if (cudaMalloc((void**)&q->d_bits, bits.size() * 4) != cudaSuccess ||
+      cudaMemcpy(q->d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete q;
+    return fail(BFTQ_ERR_CUDA, "quorum upload failed");
+  }
+  q->dev.member_bits = q->d_bits;
+  *out = q;
+  return BFTQ_OK;
+}
+
+void bftq_quorum_destroy(bftq_engine* e, bftq_quorum* q) {
+  if (!q) return;
+  if (e) cudaSetDevice(e->device);
+  if (q->d_bits) { cudaDeviceSynchronize(); cudaFree(q->d_bits); }
+  delete q;
+}
+
+static int tally_host(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx, const uint8_t* status,
+                      const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t* out_winner, uint8_t* out_bits) {
+  if (!e || !q || !op_off || !out_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_ops == 0) return BFTQ_OK;
+  const uint64_t n_items = op_off[n_ops];
+  if (n_items && (!key_idx || !status)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (ts && value_id)
+    for (uint64_t i = 0; i < n_ops; i++)
+      if (op_off[i + 1] - op_off[i] > 32) return fail(BFTQ_ERR_INVALID_ARG, "read tally: more than 32 responders in one operation");
+  Arena a(e);
+  uint32_t *d_off, *d_idx, *d_val = nullptr, *d_win = nullptr; uint8_t *d_st, *d_bits; uint64_t* d_ts = nullptr;
+  a.in(&d_off, op_off, (size_t)n_ops + 1);
+  a.in(&d_idx, key_idx, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
+  a.in(&d_st, status, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
+  if (ts && value_id) {
+    a.in(&d_ts, ts, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
+    a.in(&d_val, value_id, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
+    a.out(&d_win, out_winner, (size_t)n_ops);
+  }
+  a.out(&d_bits, out_bits, (size_t)n_ops);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = launch_tally(e, q, d_off, d_idx, d_st, d_ts, d_val, n_ops, d_win, d_bits, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
+int bftq_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                     const uint8_t* status, uint64_t n_ops, uint8_t* out_bits) {
+  return tally_host(e, q, op_off, key_idx, status, nullptr, nullptr, n_ops, nullptr, out_bits);
+}
+
+int bftq_read_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                          const uint8_t* status, const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops,
+                          uint32_t* out_winner, uint8_t* out_bits) {
+  if (!ts || !value_id || !out_winner) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  return tally_host(e, q, op_off, key_idx, status, ts, value_id, n_ops, out_winner, out_bits);
+}
+
+int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                                const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg,
+                                const uint8_t* d_pre_status, const uint64_t* d_ts, const uint32_t* d_value_id,
+                                uint64_t n_ops, uint64_t n_items, uint32_t flags, uint8_t* d_status, uint8_t* d_bits,
+                                uint32_t* d_winner, void* cuda_stream) {
+  if (!e || !q || !d_op_off || !d_status || !d_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (bftq::host_hash_dlen(hash_alg) == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
+  if (n_ops == 0) return BFTQ_OK;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (n_items) {
+    if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
+    int rc = launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_pre_status, d_status, st);
+    if (rc) return rc;
+  }
+  return launch_tally(e, q, d_op_off, d_key_idx, d_status, d_ts, d_value_id, n_ops, d_winner, d_bits, st);
+}
+
+int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                            const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
+                            const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
+                            uint8_t* out_status, uint8_t* out_bits, uint32_t* out_winner) {
+  if (!e || !q || !op_off || !out_status || !out_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  const int dlen = bftq::host_hash_dlen(hash_alg);
+  if (dlen == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
+  if (n_ops == 0) return BFTQ_OK;
+  const uint64_t n_items = op_off[n_ops];
+  if (n_items && (!key_idx || !sig_be || !digest)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  const bool read = ts && value_id;
+  if (read) {
+    if (!out_winner) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n_ops; i++)
+      if (op_off[i + 1] - op_off[i] > 32) return fail(BFTQ_ERR_INVALID_ARG, "read tally: more than 32 responders in one operation");
+  }
+  const size_t ni = (size_t)std::max<uint64_t>(n_items, 1);
+  Arena a(e);
+  uint32_t *d_off, *d_idx, *d_val = nullptr, *d_win = nullptr; uint8_t *d_sig, *d_dig, *d_pre = nullptr, *d_st, *d_bits; uint64_t* d_ts = nullptr;
+  a.in(&d_sig, sig_be, ni * 256, (size_t)n_items * 256);
+  a.in(&d_dig, digest, ni * dlen, (size_t)n_items * dlen);
+  a.in(&d_off, op_off, (size_t)n_ops + 1);
+  a.in(&d_idx, key_idx, ni, (size_t)n_items);
+  if (pre_status) a.in(&d_pre, pre_status, ni, (size_t)n_items);
+  if (read) { a.in(&d_ts, ts, ni, (size_t)n_items); a.in(&d_val, value_id, ni, (size_t)n_items); a.out(&d_win, out_winner, (size_t)n_ops); }
+  a.out(&d_st, out_status, ni, (size_t)n_items);
+  a.out(&d_bits, out_bits, (size_t)n_ops);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = bftq_verify_tally_batch_dev(e, q, d_off, d_idx, d_sig, d_dig, hash_alg, d_pre, d_ts, d_val, n_ops, n_items, flags, d_st, d_bits,
+                                   d_win, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+template <int L>
+int lagrange_run(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x, const uint8_t* y_be,
+                 uint64_t n_items, uint8_t* out_be, uint8_t* out_status) {
+  bftq::LagrangeMod<L> M;
+  memset(&M, 0, sizeof(M));
+  for (uint32_t i = 0; i < mlen; i++) {
+    const uint32_t bi = mlen - 1 - i;          // little-endian byte number
+    M.m[bi >> 2] |= (uint32_t)m_be[i] << (8 * (bi & 3));
+  }
+  M.mlen = mlen;
+  uint32_t inv = M.m[0];
+  for (int i = 0; i < 5; i++) inv *= 2u - M.m[0] * inv;
+  M.m0inv = 0u - inv;
+  // R mod m by shift-and-subtract from 1
+  std::vector<uint32_t> r(L + 1, 0u);
+  r[0] = 1;
+  auto ge_m = [&](const std::vector<uint32_t>& v) {
+    if (v[L]) return true;
+    for (int i = L - 1; i >= 0; i--) if (v[i] != M.m[i]) return v[i] > M.m[i];
+    return true;
+  };
+  auto sub_m = [&](std::vector<uint32_t>& v) {
+    uint64_t br = 0;
+    for (int i = 0; i < L; i++) { uint64_t d = (uint64_t)v[i] - M.m[i] - br; v[i] = (uint32_t)d; br = (d >> 63) & 1; }
+    v[L] -= (uint32_t)br;
+  };
+  while (ge_m(r)) sub_m(r);
+  for (int b = 0; b < 32 * L; b++) {
+    for (int i = L; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+    r[0] <<= 1;
+    if (ge_m(r)) sub_m(r);
+  }
+  for (int i = 0; i < L; i++) M.r1[i] = r[i];
+  for (int b = 0; b < 32 * L; b++) {
+    for (int i = L; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+    r[0] <<= 1;
+    if (ge_m(r)) sub_m(r);
+  }
+  for (int i = 0; i < L; i++) M.r2[i] = r[i];
+  Arena a(e);
+  int32_t* d_x; uint8_t *d_y, *d_out, *d_st;
+  a.in(&d_x, x, (size_t)n_items * k);
+  a.in(&d_y, y_be, (size_t)n_items * k * mlen);
+  a.out(&d_out, out_be, (size_t)n_items * mlen);
+  a.out(&d_st, out_status, (size_t)n_items);
+  int rc = a.upload();
+  if (rc) return rc;
+  const int block = 128;
+  bftq::lagrange_combine_kernel<L><<<(unsigned)((n_items + block - 1) / block), block, 0, a.stream()>>>(M, k, d_x, d_y, n_items, d_out, d_st);
+  CU(cudaGetLastError());
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  return a.download();
+}
+}  // namespace
+
+extern "C" {
+
+int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x,
+                                const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status) {
+  if (!e || !m_be || !x || !y_be || !out_be || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (mlen == 0 || mlen > 256 || k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "modulus length must be 1..256 bytes, k 1..255");
+  if (!(m_be[mlen - 1] & 1)) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be odd");
+  bool gt1 = false;
+  for (uint32_t i = 0; i + 1 < mlen; i++) gt1 = gt1 || m_be[i];
+  if (!gt1 && m_be[mlen - 1] <= 1) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be > 1");
+  if (n_items == 0) return BFTQ_OK;
+  if (mlen <= 32) return lagrange_run<8>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
+  if (mlen <= 64) return lagrange_run<16>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
+  if (mlen <= 128) return lagrange_run<32>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
+  return lagrange_run<64>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------
+int bftq_pgp_digest_batch(bftq_engine* e, const uint8_t* data_blob, const uint64_t* data_off, uint32_t n_data,
+                          const uint32_t* data_idx, const uint8_t* suffix_blob, const uint64_t* suffix_off,
+                          uint32_t hash_alg, uint64_t n_items, uint8_t* out_digest) {
+  if (!e || !data_off || !suffix_off || !out_digest) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!bftq::digest_on_device(hash_alg)) return fail(BFTQ_ERR_INVALID_ARG, "digest algorithm not built for the device (SHA-1/224/256/384/512 are)");
+  const int dlen = bftq::host_hash_dlen(hash_alg);
+  if (n_items == 0) return BFTQ_OK;
+  if (!data_idx && n_data < n_items) return fail(BFTQ_ERR_INVALID_ARG, "data_idx is NULL but n_data < n_items");
+  if (data_idx)
+    for (uint64_t i = 0; i < n_items; i++)
+      if (data_idx[i] >= n_data) return fail(BFTQ_ERR_INVALID_ARG, "data_idx out of range");
+  const size_t dbytes = (size_t)data_off[n_data], sbytes = (size_t)suffix_off[n_items];
+  if ((dbytes && !data_blob) || (sbytes && !suffix_blob)) return fail(BFTQ_ERR_INVALID_ARG, "NULL blob");
+  Arena a(e);
+  uint8_t *d_data, *d_suf, *d_out; uint64_t *d_doff, *d_soff; uint32_t* d_didx = nullptr;
+  a.in(&d_data, data_blob, std::max<size_t>(dbytes, 1), dbytes);
+  a.in(&d_suf, suffix_blob, std::max<size_t>(sbytes, 1), sbytes);
+  a.in(&d_doff, data_off, (size_t)n_data + 1);
+  a.in(&d_soff, suffix_off, (size_t)n_items + 1);
+  if (data_idx) a.in(&d_didx, data_idx, (size_t)n_items);
+  a.out(&d_out, out_digest, (size_t)n_items * dlen);
+  int rc = a.upload();
+  if (rc) return rc;
+  CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, n_items, d_out, nullptr, nullptr, a.stream()));
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  return a.download();
+}
+
+// ---- host packer ------------------------------------------------------------------------------
+}  // extern "C"
+
+struct bftq_keyring {
+  bftq_engine* e = nullptr;
+  std::mutex mu;
+  std::vector<bftq::pgp::Entity> secring, keyring;
+};
+
+namespace {
+namespace pg = bftq::pgp;
+
+// Enter an RSA key in the engine's table (deduplicated).  Returns -1 when the size is not built.
+int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
+  if (!(k.algo == 1 || k.algo == 2 || k.algo == 3)) return -1;
+  if (k.nbits < 2041 || k.nbits > 2048 || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
+  std::string id((const char*)k.n_be.data(), k.n_be.size());
+  id.append((const char*)&k.e, 4);
   {
     std::lock_guard<std::mutex> g(e->mu);
-    e->stats.h2d_bytes += sig_b + dig_b + idx_b;
-    e->stats.d2h_bytes += n_items;
+    auto it = e->key_lookup.find(id);
+    if (it != e->key_lookup.end()) return (int32_t)it->second;
   }
+  uint8_t n_be[256];
+  memset(n_be, 0, 256);
+  memcpy(n_be + 256 - k.n_be.size(), k.n_be.data(), k.n_be.size());
+  uint32_t first = 0;
+  if (bftq_register_rsa_keys(e, n_be, &k.e, 1, &first) != BFTQ_OK) return -1;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->key_lookup[id] = first;
+  return (int32_t)first;
+}
+void index_entity_keys(bftq_engine* e, pg::Entity& ent) {
+  ent.primary.table_idx = engine_key_index(e, ent.primary);
+  for (auto& sk : ent.subkeys) sk.key.table_idx = engine_key_index(e, sk.key);
+}
+
+struct Tuple {
+  uint32_t item, call;
+  int32_t key_idx;
+  uint64_t signer_id;          // primary key id of the candidate key's entity
+  uint8_t pre;                 // status decided on the host (0 = ask the GPU)
+  uint8_t hash_id;
+  uint16_t tag;
+  uint32_t data_idx;
+  uint32_t suffix_pos, suffix_len;   // into suffix blob
+  uint8_t sig[256];
+};
+struct Plan {
+  std::vector<Tuple> tuples;
+  std::vector<uint32_t> calls_per_item;     // number of CheckDetachedSignature calls that reached a known issuer
+  std::vector<uint8_t> item_failed;          // Verify mode: a structural error / unknown issuer ended the stream
+  std::vector<uint8_t> suffix_blob;
+  std::vector<uint8_t> data_blob;            // tbs strings, plus CRLF-canonicalised copies when needed
+  std::vector<uint64_t> data_off;
+};
+
+void canonical_text(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
+  for (size_t i = 0; i < n; i++) {
+    if (d[i] == 0x0d && i + 1 < n && d[i + 1] == 0x0a) { out.push_back(0x0d); out.push_back(0x0a); i++; }
+    else if (d[i] == 0x0a) { out.push_back(0x0d); out.push_back(0x0a); }
+    else out.push_back(d[i]);
+  }
+}
+
+// Parses item `i`'s signature stream against `rings`.  collective = CollectiveSignature.Verify's
+// tolerant loop (crypto_pgp.go:485-500), else Signature.Verify's strict one (:319-330).
+void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, const uint8_t* sig, size_t sig_len,
+               const std::vector<const std::vector<pg::Entity>*>& rings, bool collective) {
+  const uint32_t data_plain = (uint32_t)pl.data_off.size() - 1;
+  pl.data_blob.insert(pl.data_blob.end(), tbs, tbs + tbs_len);
+  pl.data_off.push_back(pl.data_blob.size());
+  int32_t data_text = -1;
+  pg::Reader r{sig, sig_len, 0};
+  std::vector<uint8_t> scratch;
+  std::vector<pg::KeyRef> keys;
+  pg::SigPacket sp;
+  uint32_t calls = 0;
+  bool failed = false;
+  while (r.remaining() > 0) {
+    const int rc = pg::next_known_signature(r, rings, sp, keys, scratch);
+    if (rc == pg::kOk) {
+      const uint32_t spos = (uint32_t)pl.suffix_blob.size();
+      pl.suffix_blob.insert(pl.suffix_blob.end(), sp.suffix.begin(), sp.suffix.end());
+      uint32_t didx = data_plain;
+      uint8_t common_pre = 0;
+      if (sp.version != 4) common_pre = BFTQ_ST_UNSUPPORTED;                    // SignatureV3: not built
+      else if (sp.sig_type == 0x01) {
+        if (data_text < 0) {
+          std::vector<uint8_t> t;
+          canonical_text(tbs, tbs_len, t);
+          data_text = (int32_t)pl.data_off.size() - 1;
+          pl.data_blob.insert(pl.data_blob.end(), t.begin(), t.end());
+          pl.data_off.push_back(pl.data_blob.size());
+        }
+        didx = (uint32_t)data_text;
+      } else if (sp.sig_type != 0x00) common_pre = BFTQ_ST_BAD_SIGNATURE;       // hashForSignature: unsupported type
+      if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3)) common_pre = BFTQ_ST_UNSUPPORTED;   // DSA / ECDSA: not built
+      if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // MD5 / RIPEMD-160: not built
+      if (!common_pre && sp.mpi.size() > 256) common_pre = BFTQ_ST_BAD_SIGNATURE;                    // len(sig) != k
+      for (const pg::KeyRef& kr : keys) {
+        Tuple t;
+        memset(&t, 0, sizeof(t));
+        t.item = item; t.call = calls; t.signer_id = kr.entity->primary.key_id;
+        t.tag = (uint16_t)((sp.hash_tag[0] << 8) | sp.hash_tag[1]);
+        t.data_idx = didx; t.suffix_pos = spos; t.suffix_len = (uint32_t)sp.suffix.size();
+        t.pre = common_pre;
+        t.hash_id = sp.hash_id;
+        t.key_idx = kr.key->table_idx;
+        if (!t.pre && kr.key->algo != sp.pk_algo) t.pre = BFTQ_ST_BAD_SIGNATURE;   // "different algorithms"
+        if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
+        if (t.key_idx < 0) t.key_idx = 0;
+        if (sp.mpi.size() <= 256) memcpy(t.sig + 256 - sp.mpi.size(), sp.mpi.data(), sp.mpi.size());   // padToKeySize
+        pl.tuples.push_back(t);
+      }
+      calls++;
+    } else if (collective) {
+      continue;                      // errors are ignored; the offending packet (or the rest) was consumed
+    } else {
+      failed = true;
+      break;
+    }
+  }
+  pl.calls_per_item.push_back(calls);
+  pl.item_failed.push_back(failed ? 1 : 0);
+}
+
+// digest (K4) -> tag check -> RSA verify (K1) for every tuple of the plan; tuples are grouped by hash
+// algorithm (digest length differs), each group is one K4 + one K1 launch on one stream.
+int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, std::vector<uint8_t>& status) {
+  const size_t nt = sel.size();
+  const int dlen = bftq::host_hash_dlen(hash_alg);
+  std::vector<uint32_t> key_idx(nt), data_idx(nt);
+  std::vector<uint16_t> tags(nt);
+  std::vector<uint8_t> pre(nt), sigs(nt * 256), st(nt);
+  std::vector<uint64_t> soff(nt + 1);
+  std::vector<uint8_t> sblob;
+  for (size_t i = 0; i < nt; i++) {
+    const Tuple& t = pl.tuples[sel[i]];
+    key_idx[i] = (uint32_t)t.key_idx; data_idx[i] = t.data_idx; tags[i] = t.tag; pre[i] = t.pre;
+    memcpy(&sigs[i * 256], t.sig, 256);
+    soff[i] = sblob.size();
+    sblob.insert(sblob.end(), pl.suffix_blob.begin() + t.suffix_pos, pl.suffix_blob.begin() + t.suffix_pos + t.suffix_len);
+  }
+  soff[nt] = sblob.size();
+  if (!e->d_keys || !bftq::digest_on_device(hash_alg)) {   // nothing verifiable: every tuple keeps its host status
+    for (size_t i = 0; i < nt; i++) status[sel[i]] = pre[i] ? pre[i] : (uint8_t)BFTQ_ST_UNSUPPORTED;
+    return BFTQ_OK;
+  }
+  Arena a(e);
+  uint8_t *d_data, *d_suf, *d_pre, *d_sig, *d_dig, *d_st; uint64_t *d_doff, *d_soff; uint32_t *d_didx, *d_kidx; uint16_t* d_tags;
+  a.in(&d_data, pl.data_blob.data(), std::max<size_t>(pl.data_blob.size(), 1), pl.data_blob.size());
+  a.in(&d_doff, pl.data_off.data(), pl.data_off.size());
+  a.in(&d_suf, sblob.data(), std::max<size_t>(sblob.size(), 1), sblob.size());
+  a.in(&d_soff, soff.data(), soff.size());
+  a.in(&d_didx, data_idx.data(), nt);
+  a.in(&d_kidx, key_idx.data(), nt);
+  a.in(&d_tags, tags.data(), nt);
+  a.in(&d_pre, pre.data(), nt);
+  a.in(&d_sig, sigs.data(), nt * 256);
+  a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
+  a.out(&d_st, st.data(), nt);
+  int rc = a.upload();
+  if (rc) return rc;
+  CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, nt, d_dig, d_tags, d_pre, a.stream()));
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream());
+  if (rc) return rc;
+  rc = a.download();
+  if (rc) return rc;
+  for (size_t i = 0; i < nt; i++) status[sel[i]] = st[i];
+  return BFTQ_OK;
+}
+
+int run_plan(bftq_engine* e, Plan& pl, std::vector<uint8_t>& status) {
+  status.assign(pl.tuples.size(), 0);
+  std::map<uint32_t, std::vector<uint32_t>> groups;
+  for (size_t i = 0; i < pl.tuples.size(); i++) groups[pl.tuples[i].hash_id].push_back((uint32_t)i);
+  for (auto& g : groups) {
+    int rc = run_plan_group(e, pl, g.second, g.first, status);
+    if (rc) return rc;
+  }
+  return BFTQ_OK;
+}
+
+// Per item: did call c succeed (any candidate tuple verified) and who signed.
+struct CallResult { bool ok; uint64_t signer; };
+void fold_calls(const Plan& pl, const std::vector<uint8_t>& status, std::vector<std::vector<CallResult>>& out) {
+  out.assign(pl.calls_per_item.size(), {});
+  for (size_t i = 0; i < out.size(); i++) out[i].assign(pl.calls_per_item[i], CallResult{false, 0});
+  for (size_t t = 0; t < pl.tuples.size(); t++) {
+    const Tuple& tp = pl.tuples[t];
+    CallResult& cr = out[tp.item][tp.call];
+    if (!cr.ok && status[t] == 0) { cr.ok = true; cr.signer = tp.signer_id; }
+  }
+}
+
+int check_blobs(const void* blob, const uint64_t* off, uint64_t n) {
+  if (!off) return 1;
+  for (uint64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return 1;
+  if (off[n] > off[0] && !blob) return 1;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int bftq_keyring_create(bftq_engine* e, bftq_keyring** out) {
+  if (!e || !out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  auto* kr = new bftq_keyring();
+  kr->e = e;
+  *out = kr;
+  return BFTQ_OK;
+}
+void bftq_keyring_destroy(bftq_keyring* kr) { delete kr; }
+
+int bftq_keyring_add(bftq_keyring* kr, const uint8_t* key_blocks, uint64_t len, int priv, uint32_t* n_entities) {
+  if (!kr || (len && !key_blocks)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<pg::Entity> ents;
+  pg::read_entities(key_blocks, (size_t)len, ents);
+  for (auto& en : ents) index_entity_keys(kr->e, en);
+  std::lock_guard<std::mutex> g(kr->mu);
+  auto& ring = priv ? kr->secring : kr->keyring;
+  for (auto& en : ents) {                                     // replace(), crypto_pgp.go:124-140
+    bool replaced = false;
+    for (auto& old : ring) if (old.primary.key_id == en.primary.key_id) { old = en; replaced = true; break; }
+    if (!replaced) ring.push_back(en);
+  }
+  if (n_entities) *n_entities = (uint32_t)ents.size();
+  return BFTQ_OK;
+}
+
+int bftq_keyring_remove(bftq_keyring* kr, const uint64_t* key_ids, uint32_t n) {
+  if (!kr || (n && !key_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> g(kr->mu);
+  std::vector<pg::Entity> keep;
+  for (auto& en : kr->keyring) {
+    bool drop = false;
+    for (uint32_t i = 0; i < n; i++) drop = drop || key_ids[i] == en.primary.key_id;
+    if (!drop) keep.push_back(en);
+  }
+  kr->keyring.swap(keep);
+  return BFTQ_OK;
+}
+
+int bftq_keyring_ids(bftq_keyring* kr, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
+  if (!kr || !n) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> g(kr->mu);
+  uint32_t c = 0;
+  for (auto* ring : {&kr->secring, &kr->keyring})
+    for (auto& en : *ring) { if (out_ids && c < cap) out_ids[c] = en.primary.key_id; c++; }
+  *n = c;
+  return BFTQ_OK;
+}
+
+int bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
+  if (!kr || !n) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> g(kr->mu);
+  *n = 0;
+  for (auto* ring : {&kr->keyring, &kr->secring})            // getCertById order, crypto_pgp.go:206-219
+    for (auto& en : *ring)
+      if (en.primary.key_id == key_id) {
+        uint32_t c = 0;
+        for (uint64_t id : en.certifiers) { if (out_ids && c < cap) out_ids[c] = id; c++; }
+        *n = c;
+        return BFTQ_OK;
+      }
+  return fail(BFTQ_ERR_INVALID_ARG, "key id not in keyring");
+}
+
+static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
+                             const uint64_t* sig_off, const uint8_t* cert_blob, const uint64_t* cert_off, uint64_t n_items,
+                             int32_t* out_err) {
+  if (!kr || !out_err) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(sig_blob, sig_off, n_items) || (cert_off && check_blobs(cert_blob, cert_off, n_items)))
+    return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
+  if (n_items == 0) return BFTQ_OK;
+  Plan pl;
+  pl.data_off.push_back(0);
+  std::vector<std::vector<pg::Entity>> cert_rings;          // one single-entity ring per item (VerifyWithCertificate)
+  std::vector<pg::Entity> sec, pub;
+  if (cert_off) {
+    cert_rings.resize(n_items);
+    for (uint64_t i = 0; i < n_items; i++) {
+      std::vector<pg::Entity> ents;
+      pg::read_entities(cert_blob + cert_off[i], (size_t)(cert_off[i + 1] - cert_off[i]), ents);
+      if (!ents.empty()) { index_entity_keys(kr->e, ents[0]); cert_rings[i].push_back(ents[0]); }
+    }
+  } else {
+    std::lock_guard<std::mutex> g(kr->mu);
+    sec = kr->secring; pub = kr->keyring;
+  }
+  for (uint64_t i = 0; i < n_items; i++) {
+    std::vector<const std::vector<pg::Entity>*> rings;
+    if (cert_off) rings = {&cert_rings[i]}; else rings = {&sec, &pub};
+    plan_item(pl, (uint32_t)i, tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), sig_blob + sig_off[i],
+              (size_t)(sig_off[i + 1] - sig_off[i]), rings, false);
+  }
+  std::vector<uint8_t> status;
+  int rc = run_plan(kr->e, pl, status);
+  if (rc) return rc;
+  std::vector<std::vector<CallResult>> calls;
+  fold_calls(pl, status, calls);
+  for (uint64_t i = 0; i < n_items; i++) {
+    bool ok = !pl.item_failed[i] && !calls[i].empty();       // "at least we need one valid signature"
+    for (auto& c : calls[i]) ok = ok && c.ok;
+    if (cert_off && cert_rings[i].empty()) ok = false;
+    out_err[i] = ok ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
+  }
+  return BFTQ_OK;
+}
+
+int bftq_signature_verify_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
+                                const uint64_t* sig_off, uint64_t n_items, int32_t* out_err) {
+  return verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, nullptr, nullptr, n_items, out_err);
+}
+int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
+                                          const uint8_t* sig_blob, const uint64_t* sig_off, const uint8_t* cert_blob,
+                                          const uint64_t* cert_off, uint64_t n_items, int32_t* out_err) {
+  if (!cert_off) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  return verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, cert_blob, cert_off, n_items, out_err);
+}
+
+// Signers(): every parseable v4 signature packet whose issuer is a PRIMARY key id of the keyring.
+static int signers_impl(bftq_keyring* kr, const uint8_t* sig, uint64_t len, std::vector<uint64_t>& ids) {
+  std::vector<pg::Entity> sec, pub;
+  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
+  pg::Reader r{sig, (size_t)len, 0};
+  std::vector<uint8_t> scratch;
+  for (;;) {
+    int tag; const uint8_t* body; size_t bl;
+    const int rc = pg::read_packet(r, tag, body, bl, scratch);
+    if (rc) break;                                            // EOF or framing error ends r.Next()'s loop
+    if (!pg::known_tag(tag) || tag != 2) continue;
+    pg::SigPacket sp;
+    if (pg::parse_signature(body, bl, sp)) break;             // parse error: r.Next() returns err -> break
+    if (sp.version != 4) continue;                            // *SignatureV3 is not in the type switch
+    if (!sp.has_issuer) return fail(BFTQ_ERR_MALFORMED, "signature without issuer (the reference dereferences nil here)");
+    bool found = false;                                       // getCertById: keyring first, then secring
+    for (auto& en : pub) found = found || en.primary.key_id == sp.issuer;
+    for (auto& en : sec) found = found || en.primary.key_id == sp.issuer;
+    if (found) ids.push_back(sp.issuer);
+  }
+  return BFTQ_OK;
+}
+
+int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
+  if (!kr || !n || (sig_len && !sig)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<uint64_t> ids;
+  int rc = signers_impl(kr, sig, sig_len, ids);
+  if (rc) return rc;
+  for (uint32_t i = 0; i < ids.size() && i < cap && out_ids; i++) out_ids[i] = ids[i];
+  *n = (uint32_t)ids.size();
+  return BFTQ_OK;
+}
+
+// Node ids -> dense indices, quorum by index, GPU tally (K2) over the verified signers.
+static int sufficient_by_tally(bftq_engine* e, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids, uint32_t n_members,
+                               const std::vector<std::vector<uint64_t>>& signers, std::vector<uint8_t>& bits) {
+  std::map<uint64_t, uint32_t> dense;
+  auto idx_of = [&](uint64_t id) { auto it = dense.find(id); if (it != dense.end()) return it->second; uint32_t v = (uint32_t)dense.size(); dense[id] = v; return v; };
+  std::vector<bftq_qc_t> q(n_qc);
+  std::vector<uint32_t> members(n_members);
+  for (uint32_t m = 0; m < n_members; m++) members[m] = idx_of(member_ids[m]);
+  for (uint32_t c = 0; c < n_qc; c++) q[c] = bftq_qc_t{qcs[c].f, qcs[c].min, qcs[c].threshold, qcs[c].suff, qcs[c].member_off, qcs[c].member_cnt};
+  bftq_quorum* qh = nullptr;
+  int rc = bftq_quorum_create(e, q.data(), n_qc, members.data(), n_members, &qh);
+  if (rc) return rc;
+  std::vector<uint32_t> off(signers.size() + 1, 0), kidx;
+  for (size_t i = 0; i < signers.size(); i++) {
+    for (uint64_t id : signers[i]) kidx.push_back(idx_of(id));
+    off[i + 1] = (uint32_t)kidx.size();
+  }
+  std::vector<uint8_t> st(std::max<size_t>(kidx.size(), 1), 0);
+  if (kidx.empty()) kidx.push_back(0);
+  bits.assign(signers.size(), 0);
+  rc = bftq_tally_batch(e, qh, off.data(), kidx.data(), st.data(), signers.size(), bits.data());
+  bftq_quorum_destroy(e, qh);
+  return rc;
+}
+
+int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
+                                 uint32_t n_members, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* ss_blob,
+                                 const uint64_t* ss_off, uint64_t n_items, int32_t* out_err) {
+  if (!kr || !out_err || (n_qc && !qcs) || (n_members && !member_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(ss_blob, ss_off, n_items)) return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
+  if (n_items == 0) return BFTQ_OK;
+  std::vector<pg::Entity> sec, pub;
+  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
+  std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
+  Plan pl;
+  pl.data_off.push_back(0);
+  for (uint64_t i = 0; i < n_items; i++)
+    plan_item(pl, (uint32_t)i, tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), ss_blob + ss_off[i],
+              (size_t)(ss_off[i + 1] - ss_off[i]), rings, true);
+  std::vector<uint8_t> status;
+  int rc = run_plan(kr->e, pl, status);
+  if (rc) return rc;
+  std::vector<std::vector<CallResult>> calls;
+  fold_calls(pl, status, calls);
+  std::vector<std::vector<uint64_t>> signers(n_items);
+  for (uint64_t i = 0; i < n_items; i++)
+    for (auto& c : calls[i]) if (c.ok) signers[i].push_back(c.signer);      // no dedupe (crypto_pgp.go:492)
+  std::vector<uint8_t> bits;
+  rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
+  if (rc) return rc;
+  for (uint64_t i = 0; i < n_items; i++) out_err[i] = (bits[i] & BFTQ_TALLY_IS_SUFFICIENT) ? 0 : BFTQ_ERR_INSUFFICIENT_SIGS;
+  return BFTQ_OK;
+}
+
+int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
+                                       uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out) {
+  if (!kr || !out || (ss_len && !ss)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<std::vector<uint64_t>> signers(1);
+  int rc = signers_impl(kr, ss, ss_len, signers[0]);
+  if (rc) return rc;
+  std::vector<uint8_t> bits;
+  rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
+  if (rc) return rc;
+  *out = (bits[0] & BFTQ_TALLY_IS_SUFFICIENT) ? 1 : 0;
   return BFTQ_OK;
 }
 

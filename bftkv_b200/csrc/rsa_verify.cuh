@@ -172,7 +172,8 @@ template <int T, int W, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, const uint32_t* __restrict__ key_idx,
                   const uint8_t* __restrict__ sig, const uint8_t* __restrict__ digest, const uint32_t hash_alg,
-                  const uint64_t n_items, const uint32_t flags, uint8_t* __restrict__ status) {
+                  const uint64_t n_items, const uint32_t flags, const uint8_t* __restrict__ pre_status,
+                  uint8_t* __restrict__ status) {
   constexpr int kLayout = (T * W == 74) ? 0 : ((T * W == 76) ? 1 : 2);
   static_assert(T * W == 74 || T * W == 76 || T * W == 80, "unsupported digit layout");
   constexpr int kGroupsPerWarp = 32 / T;
@@ -291,6 +292,10 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
       uint8_t st = (eqb == gmask) ? (uint8_t)0 : (uint8_t)1;         // BFTQ_ST_OK / BFTQ_ST_BAD_SIGNATURE
       if ((flags & 1u) && s_ge_n) st = 1;                             // BFTQ_F_STRICT_RANGE
       if (!known) st = 4;                                             // BFTQ_ST_UNKNOWN_SIGNER
+      if (pre_status != nullptr) {                                    // decided by the packer (missing, malformed ...)
+        const uint8_t pre = __ldg(pre_status + item_raw);
+        if (pre != 0) st = pre;
+      }
       status[item_raw] = st;
     }
   }

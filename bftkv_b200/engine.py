@@ -10,7 +10,18 @@ ST_OK, ST_BAD_SIGNATURE, ST_HASH_TAG, ST_MALFORMED, ST_UNKNOWN_SIGNER, ST_UNSUPP
 DIGEST_LEN = {1: 16, 2: 20, 3: 20, 8: 32, 9: 48, 10: 64, 11: 28}
 
 
+class QC(C.Structure):
+    _fields_ = [("f", C.c_int32), ("min", C.c_int32), ("threshold", C.c_int32), ("suff", C.c_int32),
+                ("member_off", C.c_uint32), ("member_cnt", C.c_uint32)]
+
+
+TALLY_IS_QUORUM, TALLY_IS_THRESHOLD, TALLY_IS_SUFFICIENT, TALLY_REJECT = 1, 2, 4, 8
+NO_WINNER = 0xFFFFFFFF
+
+
 def _ptr(a):
+    if a is None:
+        return C.c_void_p(0)
     if isinstance(a, np.ndarray):
         assert a.flags["C_CONTIGUOUS"]
         return C.c_void_p(a.ctypes.data)
@@ -71,6 +82,83 @@ class Engine:
     def rsa_verify_batch_dev(self, d_key_idx, d_sig, d_digest, n, d_status, hash_alg=HASH_SHA256, flags=0, stream=0):
         _lib.check(self._lib.bftq_rsa_verify_batch_dev(self._h, _ptr(d_key_idx), _ptr(d_sig), _ptr(d_digest),
                                                        hash_alg, n, flags, _ptr(d_status), C.c_void_p(stream)))
+
+    # ---- K2 ----
+    def quorum_create(self, qcs):
+        """qcs: list of (f, min, threshold, suff, [member key indices]).  Returns an opaque handle."""
+        arr = (QC * max(1, len(qcs)))()
+        members, off = [], 0
+        for i, (f, mn, th, sf, mem) in enumerate(qcs):
+            arr[i] = QC(f, mn, th, sf, off, len(mem))
+            members += list(mem)
+            off += len(mem)
+        m = np.asarray(members if members else [0], dtype=np.uint32)
+        h = C.c_void_p()
+        _lib.check(self._lib.bftq_quorum_create(self._h, C.cast(arr, C.c_void_p), len(qcs), _ptr(m), len(members), C.byref(h)))
+        return h
+
+    def quorum_destroy(self, q):
+        self._lib.bftq_quorum_destroy(self._h, q)
+
+    def tally_batch(self, q, op_off, key_idx, status):
+        n_ops = int(op_off.shape[0]) - 1
+        out = np.empty(n_ops, np.uint8)
+        _lib.check(self._lib.bftq_tally_batch(self._h, q, _ptr(op_off), _ptr(key_idx), _ptr(status), n_ops, _ptr(out)))
+        return out
+
+    def read_tally_batch(self, q, op_off, key_idx, status, ts, value_id):
+        n_ops = int(op_off.shape[0]) - 1
+        win, bits = np.empty(n_ops, np.uint32), np.empty(n_ops, np.uint8)
+        _lib.check(self._lib.bftq_read_tally_batch(self._h, q, _ptr(op_off), _ptr(key_idx), _ptr(status), _ptr(ts), _ptr(value_id),
+                                                   n_ops, _ptr(win), _ptr(bits)))
+        return win, bits
+
+    def verify_tally_batch(self, q, op_off, key_idx, sig_be, digest, pre_status=None, ts=None, value_id=None,
+                           hash_alg=HASH_SHA256, flags=0, out_status=None, out_bits=None, out_winner=None):
+        n_ops = int(op_off.shape[0]) - 1
+        n_items = int(key_idx.shape[0])
+        st = out_status if out_status is not None else np.empty(max(n_items, 1), np.uint8)
+        bits = out_bits if out_bits is not None else np.empty(n_ops, np.uint8)
+        win = out_winner if out_winner is not None else (np.empty(n_ops, np.uint32) if ts is not None else None)
+        _lib.check(self._lib.bftq_verify_tally_batch(self._h, q, _ptr(op_off), _ptr(key_idx), _ptr(sig_be), _ptr(digest), hash_alg,
+                                                     _ptr(pre_status), _ptr(ts), _ptr(value_id), n_ops, flags, _ptr(st), _ptr(bits),
+                                                     _ptr(win)))
+        return (st[:n_items] if out_status is None else st), bits, win
+
+    def verify_tally_batch_dev(self, q, d_op_off, d_key_idx, d_sig, d_digest, n_ops, n_items, d_status, d_bits, d_pre=None,
+                               d_ts=None, d_value_id=None, d_winner=None, hash_alg=HASH_SHA256, flags=0, stream=0):
+        _lib.check(self._lib.bftq_verify_tally_batch_dev(self._h, q, _ptr(d_op_off), _ptr(d_key_idx), _ptr(d_sig), _ptr(d_digest),
+                                                         hash_alg, _ptr(d_pre), _ptr(d_ts), _ptr(d_value_id), n_ops, n_items, flags,
+                                                         _ptr(d_status), _ptr(d_bits), _ptr(d_winner), C.c_void_p(stream)))
+
+    # ---- K3 ----
+    def lagrange_combine_batch(self, m: int, x, y_be):
+        """m: odd modulus (int); x: (B,k) int32; y_be: (B,k,mlen) uint8 big-endian.  Returns (out (B,mlen), status (B,))."""
+        mlen = (m.bit_length() + 7) // 8
+        x = np.ascontiguousarray(x, np.int32)
+        y_be = np.ascontiguousarray(y_be, np.uint8)
+        B, k = x.shape
+        assert y_be.shape == (B, k, mlen)
+        mb = np.frombuffer(m.to_bytes(mlen, "big"), np.uint8).copy()
+        out, st = np.empty((B, mlen), np.uint8), np.empty(B, np.uint8)
+        _lib.check(self._lib.bftq_lagrange_combine_batch(self._h, _ptr(mb), mlen, k, _ptr(x), _ptr(y_be), B, _ptr(out), _ptr(st)))
+        return out, st
+
+    # ---- K4 ----
+    def pgp_digest_batch(self, datas, suffixes, data_idx=None, hash_alg=HASH_SHA256):
+        """datas: list of bytes (TBS strings); suffixes: list of bytes (one per signature)."""
+        n = len(suffixes)
+        doff = np.zeros(len(datas) + 1, np.uint64)
+        doff[1:] = np.cumsum([len(d) for d in datas])
+        soff = np.zeros(n + 1, np.uint64)
+        soff[1:] = np.cumsum([len(s) for s in suffixes])
+        dblob = np.frombuffer(b"".join(datas) or b"\0", np.uint8).copy()
+        sblob = np.frombuffer(b"".join(suffixes) or b"\0", np.uint8).copy()
+        didx = None if data_idx is None else np.ascontiguousarray(data_idx, np.uint32)
+        out = np.empty((n, DIGEST_LEN[hash_alg]), np.uint8)
+        _lib.check(self._lib.bftq_pgp_digest_batch(self._h, _ptr(dblob), _ptr(doff), len(datas), _ptr(didx), _ptr(sblob), _ptr(soff),
+                                                   hash_alg, n, _ptr(out)))
+        return out
 
     def stats(self):
         s = _lib.Stats()

@@ -84,3 +84,35 @@ def make_verify_batch(n_items: int, n_keys: int = 16, seed: int = 0xBF7C0002, co
 
 def em_for_digest(digest: bytes) -> int:
     return int.from_bytes(b"\x00\x01" + b"\xff" * 202 + b"\x00" + SHA256_PREFIX + digest, "big")
+
+
+def make_read_ops(pool, n_ops: int, n_replicas: int, seed: int = 0xBF7C0004, p_ok=0.90, p_stale=0.05, p_bad=0.03):
+    """Configs 3 / 5: M read ops x R replicas.  Replica r of every op answers with key r.  Each
+    response is (valid, current value) w.p. p_ok, (valid, stale t) p_stale, invalid signature p_bad,
+    missing otherwise.  Signed tuples are drawn from `pool` (make_verify_batch output
+    with n_keys == n_replicas, no corruption): slot (op, r) takes a pool item signed by key r, so
+    every signature is genuine; uniqueness across ops is limited by the pool size (stated in
+    bench.py's `data`).  Returns op_off, key_idx, sig, digest, pre_status, ts, value_id and the
+    expected per-item status."""
+    rng = np.random.default_rng(seed)
+    R, M = n_replicas, n_ops
+    by_key = [np.nonzero(pool["key_idx"] == r)[0] for r in range(R)]
+    assert all(len(b) for b in by_key), "pool lacks items for some replica key"
+    N = M * R
+    key_idx = np.tile(np.arange(R, dtype=np.uint32), M)
+    pick = np.empty(N, np.int64)
+    for r in range(R):
+        pick[r::R] = by_key[r][rng.integers(0, len(by_key[r]), M)]
+    sig = pool["sig"][pick].copy()
+    digest = pool["digest"][pick].copy()
+    u = rng.random(N)
+    kind = np.where(u < p_ok, 0, np.where(u < p_ok + p_stale, 1, np.where(u < p_ok + p_stale + p_bad, 2, 3)))
+    bad = np.nonzero(kind == 2)[0]
+    sig[bad, rng.integers(0, 256, len(bad))] ^= np.uint8(0x10)
+    pre = np.where(kind == 3, 6, 0).astype(np.uint8)                  # BFTQ_ST_MISSING
+    ts = np.where(kind == 1, 6, 7).astype(np.uint64)                  # stale replicas are one write behind
+    value_id = np.where(kind == 1, 1, 0).astype(np.uint32)
+    expect = np.where(kind == 2, 1, pre).astype(np.uint8)
+    op_off = (np.arange(M + 1, dtype=np.uint64) * R).astype(np.uint32)
+    return {"op_off": op_off, "key_idx": key_idx, "sig": sig, "digest": digest, "pre_status": pre, "ts": ts,
+            "value_id": value_id, "expect_status": expect}

@@ -112,6 +112,142 @@ int bftq_rsa_verify_batch_dev(bftq_engine* e, const uint32_t* d_key_idx, const u
                               const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items,
                               uint32_t flags, uint8_t* d_status, void* cuda_stream);
 
+/* ---- K2: batched wotqs quorum tally ---------------------------------------------------------
+ * A quorum descriptor is what wotqs.getQuorumFrom builds (quorum/wotqs/wotqs.go:95-115): a list of
+ * quorum cliques qc{nodes,f,min,threshold,suff} (wotqs.go:16-22, values from newQC :36-70).
+ * Members are given as KEY-TABLE INDICES (the shim maps node.Id() -> index once per keyring
+ * version); member_key_idx[member_off .. member_off+member_cnt) belongs to clique i. */
+typedef struct {
+  int32_t f, min, threshold, suff;
+  uint32_t member_off, member_cnt;
+} bftq_qc_t;
+typedef struct bftq_quorum bftq_quorum;
+int  bftq_quorum_create(bftq_engine* e, const bftq_qc_t* qcs, uint32_t n_qc, const uint32_t* member_key_idx,
+                        uint32_t n_members, bftq_quorum** out);
+void bftq_quorum_destroy(bftq_engine* e, bftq_quorum* q);
+
+/* Tally bits written per operation */
+#define BFTQ_TALLY_IS_QUORUM      0x01  /* wotqs.go:144-155 */
+#define BFTQ_TALLY_IS_THRESHOLD   0x02  /* wotqs.go:157-167 */
+#define BFTQ_TALLY_IS_SUFFICIENT  0x04  /* wotqs.go:169-176 */
+#define BFTQ_TALLY_REJECT         0x08  /* wotqs.go:178-185, evaluated over the FAILED responders */
+#define BFTQ_NO_WINNER            0xffffffffu
+
+/* Replaces Quorum.IsQuorum/IsThreshold/IsSufficient/Reject (quorum/quorum.go:18-25) as the
+ * multicast callbacks call them after every response (protocol/client.go:74,77,111,113,153).
+ * Operation i owns responders [op_off[i], op_off[i+1]); responder p = (key_idx[p], status[p]).
+ * status 0 = verified response -> counted in the `nodes` list; any other status -> `failure`
+ * list.  Duplicated responders count as often as they occur (wotqs.go:195-206).  Host buffers. */
+int bftq_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                     const uint8_t* status, uint64_t n_ops, uint8_t* out_bits);
+
+/* Replaces Client.maxTimestampedValue + isThreshold (protocol/client.go:181-205) over the
+ * buckets processResponse builds (:207-230): ts[p] = packet timestamp, value_id[p] = index of
+ * the distinct value inside the operation (the packer compares value bytes exactly; < 2^31).
+ * out_winner[i] = responder index (0-based inside the op) of the first member of the winning
+ * (max t, value) bucket or BFTQ_NO_WINNER (errInProgress); out_bits[i] = IS_THRESHOLD|REJECT.
+ * At most 32 responders per operation. */
+int bftq_read_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                          const uint8_t* status, const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops,
+                          uint32_t* out_winner, uint8_t* out_bits);
+
+/* K1 + K2 in one call (BASELINE configs 3 and 5: "read ops x R-replica quorum, verify + wotqs
+ * tally"): verifies all tuples, then tallies per operation on the same stream.  pre_status
+ * (nullable) carries per-tuple results decided by the packer (BFTQ_ST_MISSING, _MALFORMED,
+ * _HASH_TAG ...): non-zero entries are not verified and keep their status.  ts/value_id nullable:
+ * when given, the read tally is produced as in bftq_read_tally_batch, otherwise out_winner is
+ * not touched.  Host buffers. */
+int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                            const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
+                            const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
+                            uint8_t* out_status, uint8_t* out_bits, uint32_t* out_winner);
+/* Device-pointer form on a caller stream (no synchronisation); n_items = op_off[n_ops]. */
+int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                                const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg,
+                                const uint8_t* d_pre_status, const uint64_t* d_ts, const uint32_t* d_value_id,
+                                uint64_t n_ops, uint64_t n_items, uint32_t flags, uint8_t* d_status, uint8_t* d_bits,
+                                uint32_t* d_winner, void* cuda_stream);
+
+/* ---- K3: batched Lagrange share-combine in Z_m ----------------------------------------------
+ * Replaces sss.SSSProcess.calculateSecret / sss.Lagrange (crypto/sss/sss.go:81-107) and
+ * calculateS (crypto/threshold/dsa/dsa_core.go:389-403):  S = sum_i lambda_i(x) * y_i mod m.
+ * m_be: modulus (mlen bytes, big-endian, odd, > 1, <= 256 bytes), shared by the batch;
+ * x: n_items x k share abscissae (Coordinate.X); y_be: n_items x k x mlen share values;
+ * out_be: n_items x mlen (left-padded; the shim strips zeros where the reference returns
+ * big.Int.Bytes()); out_status: 0, or BFTQ_ST_MALFORMED when some (x_j - x_i) is not invertible
+ * mod m (the reference panics there). */
+int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x,
+                                const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status);
+
+/* ---- K4: batched OpenPGP v4 signature digest --------------------------------------------------
+ * Replaces hashForSignature + the hash-suffix step of packet.PublicKey.VerifySignature
+ * (x/crypto, reached from crypto_pgp.go:324,338,490): digest_i = H(data[data_idx[i]] || suffix_i).
+ * data blobs are the TBS/TBSS byte strings (packet/packet.go:156-190), shared by all signatures of
+ * one collective signature; suffix_i = sigpacket[0 : 6+hashedLen] || 04 FF || be32(6+hashedLen).
+ * data_off has n_data+1 entries, suffix_off n_items+1; data_idx may be NULL (identity).
+ * hash_alg: SHA-256 (what bftkv's own signer emits, crypto_pgp.go:353 with nil config), SHA-1,
+ * SHA-224, SHA-384 or SHA-512 (what foreign gpg keys may carry); MD5 / RIPEMD-160 are not built.
+ * out_digest: n_items x digest_len(hash_alg). */
+int bftq_pgp_digest_batch(bftq_engine* e, const uint8_t* data_blob, const uint64_t* data_off, uint32_t n_data,
+                          const uint32_t* data_idx, const uint8_t* suffix_blob, const uint64_t* suffix_off,
+                          uint32_t hash_alg, uint64_t n_items, uint8_t* out_digest);
+
+/* ---- host packer: the reference-facing operator interface -----------------------------------
+ * These entry points take exactly what bftkv passes to crypto.Signature /
+ * crypto.CollectiveSignature — the signed bytes and SignaturePacket.Data (raw concatenated OpenPGP
+ * signature packets, packet/packet.go:25-31) — parse them on the host, run digest + tag check +
+ * RSA verify (+ tally) on the GPU in one stream, and fold the per-tuple results back into the
+ * reference's decisions.  Blobs are concatenations with (count+1) offsets.
+ *
+ * Keyring: mirrors crypto/pgp PGPKeyring (crypto_pgp.go:115-223).  Entities are parsed from
+ * serialized OpenPGP public-key blocks (what PGPCertificate.Parse/ParseStream consume, :225-251);
+ * priv != 0 registers into the secring, which getKeyring() searches first (:195-197).  An entity
+ * whose primary key id is already present is replaced (replace(), :124-140).  RSA keys of
+ * 2041..2048 bits are also entered in the engine's key table. */
+typedef struct bftq_keyring bftq_keyring;
+int  bftq_keyring_create(bftq_engine* e, bftq_keyring** out);
+void bftq_keyring_destroy(bftq_keyring* kr);
+int  bftq_keyring_add(bftq_keyring* kr, const uint8_t* key_blocks, uint64_t len, int priv, uint32_t* n_entities);
+int  bftq_keyring_remove(bftq_keyring* kr, const uint64_t* key_ids, uint32_t n);      /* PGPKeyring.Remove :160-177 */
+/* node.Id() of every entity, secring first then keyring (getKeyring order); *n = count. */
+int  bftq_keyring_ids(bftq_keyring* kr, uint64_t* out_ids, uint32_t cap, uint32_t* n);
+/* PGPCertificateInstance.Signers (crypto_pgp.go:80-88): issuer ids of the third-party
+ * certifications on entity `key_id` (the trust-graph edges node/graph/graph.go:61-71 reads). */
+int  bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids, uint32_t cap, uint32_t* n);
+
+/* PGPSignature.Verify (crypto_pgp.go:319-330), batched over n_items independent (tbs, sig.Data)
+ * pairs: out_err[i] = 0 (nil) or BFTQ_ERR_INVALID_SIGNATURE.  Every signature packet of the
+ * stream must verify, empty data is invalid, unknown issuers are skipped unless they end the
+ * stream — exactly the reference's loop over openpgp.CheckDetachedSignature. */
+int bftq_signature_verify_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
+                                const uint8_t* sig_blob, const uint64_t* sig_off, uint64_t n_items, int32_t* out_err);
+/* PGPSignature.VerifyWithCertificate (crypto_pgp.go:332-344): the keyring of item i is the FIRST
+ * entity of cert i (Issuer(), :396-405); items with no parseable entity are invalid. */
+int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
+                                          const uint8_t* sig_blob, const uint64_t* sig_off, const uint8_t* cert_blob,
+                                          const uint64_t* cert_off, uint64_t n_items, int32_t* out_err);
+/* PGPSignature.Signers (crypto_pgp.go:373-390) for one SignaturePacket.Data: key ids of the
+ * issuers present in the keyring (primary ids via getCertById), duplicates kept, in packet order. */
+int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n);
+
+/* Quorum descriptor by node id, for the collective-signature calls (members are node.Id()s). */
+typedef struct {
+  int32_t f, min, threshold, suff;
+  uint32_t member_off, member_cnt;      /* into member_ids[] */
+} bftq_qc_ids_t;
+/* PGPCollectiveSignature.Verify (crypto_pgp.go:485-500), batched: valid packets append their
+ * signer (no dedupe), invalid / unknown ones are ignored, success as soon as q.IsSufficient
+ * (monotone, so the decision equals IsSufficient over all valid signers).  out_err[i] = 0 or
+ * BFTQ_ERR_INSUFFICIENT_SIGS; on success the shim sets ss.Completed = true (:494).  The tally runs
+ * on the GPU (K2) over the verified signers. */
+int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
+                                 uint32_t n_members, const uint8_t* tbs_blob, const uint64_t* tbs_off,
+                                 const uint8_t* ss_blob, const uint64_t* ss_off, uint64_t n_items, int32_t* out_err);
+/* PGPCollectiveSignature.Combine's decision (crypto_pgp.go:506-515) for ss.Data ++ s.Data already
+ * concatenated by the shim: q.IsSufficient(Signers(ss)) — packet parse only, no crypto. *out = 0/1. */
+int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
+                                       uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out);
+
 /* ---- statistics ------------------------------------------------------------------------------
  * Counters since bftq_init (SURVEY §5 "metrics"): items verified, kernel launches. */
 typedef struct {

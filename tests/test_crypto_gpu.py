@@ -1,0 +1,124 @@
+"""GPU suite for the reference-facing operator interface (bftkv_b200.crypto_gpu over the packer
+entry points of libbftq): Signature.Verify / VerifyWithCertificate / Signers and
+CollectiveSignature.Verify / Combine decisions must equal the oracle's restatement of
+crypto/pgp/crypto_pgp.go:319-344,373-390,485-515 on GnuPG-made inputs."""
+import numpy as np
+import pytest
+
+from bftkv_b200 import Engine
+from bftkv_b200.crypto_gpu import (CollectiveSignature, ErrInsufficientNumberOfSignatures, ErrInvalidSignature, Keyring, Quorum,
+                                   Signature)
+from oracle import packet_oracle as pk, pgp_oracle as pgp, wotqs_oracle as wq
+from oracle.wotqs_oracle import Node
+
+pytestmark = pytest.mark.gpu
+RING = ["a01", "a02", "a03", "a04", "u01"]
+
+
+@pytest.fixture(scope="module")
+def env(golden, built):
+    e = Engine(0)
+    kr = Keyring(e)
+    ents = []
+    for n in RING:
+        blob = bytes.fromhex(golden["keys"][n]["pub"])
+        assert kr.register(blob) == 1
+        ents += pgp.read_entities(blob)
+    yield {"engine": e, "kr": kr, "sig": Signature(kr), "ents": ents, "golden": golden}
+    kr.close()
+    e.close()
+
+
+def case(golden, signer, tbs_hex=None, algo="SHA256"):
+    for c in golden["cases"]:
+        if c["signer"] == signer and c["hash"] == algo and (tbs_hex is None or c["tbs"] == tbs_hex):
+            return bytes.fromhex(c["tbs"]), bytes.fromhex(c["sig"])
+    raise KeyError
+
+
+def test_keyring_mirrors_reference(env, golden):
+    ids = env["kr"].get_keyring()
+    assert ids == [int(golden["keys"][n]["key_id"], 16) for n in RING]
+    # Certificate.Signers (crypto_pgp.go:80-88): a01 is certified by a02..a04 and u01
+    cert = env["kr"].certifiers(ids[0])
+    assert sorted(cert) == sorted(int(golden["keys"][n]["key_id"], 16) for n in ["a02", "a03", "a04", "u01"])
+    assert cert == [int(c, 16) for c in golden["keys"]["a01"]["certifiers"]]
+
+
+def test_signature_verify_all_golden(env, golden):
+    cases = [c for c in golden["cases"]]
+    tbs = [bytes.fromhex(c["tbs"]) for c in cases] + [bytes.fromhex(c["tbs"]) + b"x" for c in cases]
+    sig = [bytes.fromhex(c["sig"]) for c in cases] * 2
+    got = env["sig"].verify_batch(tbs, sig)
+    ref = [pgp.signature_verify(env["ents"], t, s) for t, s in zip(tbs, sig)]
+    assert got == ref
+    assert sum(r is None for r in ref) == 41 and {c["hash"] for c in cases} == {"SHA256", "SHA512", "SHA1"}
+
+
+def test_signature_verify_stream_semantics(env, golden):
+    g = golden
+    tbs, s1 = case(g, "a01")
+    _, s2 = case(g, "a02", tbs.hex())
+    _, sx = case(g, "x99", tbs.hex())
+    bad = bytearray(s1); bad[-5] ^= 1
+    uid = bytes([0xB4, 3]) + b"abc"
+    unk = bytes([0xC0 | 60, 2, 1, 2])
+    streams = [b"", s1, s1 + s2, sx + s1, s1 + sx, bytes(bad), s1 + bytes(bad), s1[:-7], uid + s1, s1 + unk, unk + s1, s2 + s1 + s2,
+               sx, sx + sx, s1 + s1[:10]]
+    got = env["sig"].verify_batch([tbs] * len(streams), streams)
+    ref = [pgp.signature_verify(env["ents"], tbs, s) for s in streams]
+    assert got == ref
+    assert ref[:5] == [ErrInvalidSignature, None, None, None, ErrInvalidSignature]
+    # single-item entry points
+    assert env["sig"].verify(tbs, s1) is None and env["sig"].verify(tbs + b"!", s1) == ErrInvalidSignature
+    # VerifyWithCertificate: keyring = the first entity of the certificate
+    c1, c2 = bytes.fromhex(g["keys"]["a01"]["pub"]), bytes.fromhex(g["keys"]["a02"]["pub"])
+    assert env["sig"].verify_with_certificate(tbs, s1, c1) is None
+    assert env["sig"].verify_with_certificate(tbs, s1, c2) == ErrInvalidSignature
+    assert env["sig"].verify_with_certificate(tbs, s1, c2 + c1) == ErrInvalidSignature      # only the FIRST entity counts
+    assert env["sig"].verify_with_certificate(tbs, s1, b"") == ErrInvalidSignature
+    xc = bytes.fromhex(g["keys"]["x99"]["pub"])                                             # signer outside the keyring, cert supplied
+    assert env["sig"].verify_with_certificate(tbs, sx, xc) is None
+    # Signers: issuers found in the keyring, duplicates kept, unknown dropped
+    ids = {n: int(g["keys"][n]["key_id"], 16) for n in g["keys"]}
+    assert env["sig"].signers(s1 + s2 + sx + s1) == [ids["a01"], ids["a02"], ids["a01"]] == pgp.signers(env["ents"], s1 + s2 + sx + s1)
+
+
+def test_collective_signature(env, golden):
+    """Server-side write path (protocol/server.go:300): CollectiveSignature.Verify(tbss, ss, quorum)
+    for the 4-node clique of BASELINE config 1 (f=1, threshold 3, suff 3)."""
+    g = golden
+    ids = {n: int(g["keys"][n]["key_id"], 16) for n in g["keys"]}
+    clique = [ids[n] for n in ["a01", "a02", "a03", "a04"]]
+    q = Quorum(env["engine"], [(1, 4, 3, 3, clique)])
+    oq = wq.Quorum([wq.QC([Node(i) for i in clique], 1, 4, 3, 3)])
+    cs = CollectiveSignature(env["sig"])
+    tbs, s1 = case(g, "a01")
+    sigs = {n: case(g, n, tbs.hex())[1] for n in ["a01", "a02", "a03", "a04", "u01", "x99"]}
+    bad2 = bytearray(sigs["a02"]); bad2[-9] ^= 4
+    streams = [b"", sigs["a01"], sigs["a01"] + sigs["a02"], sigs["a01"] + sigs["a02"] + sigs["a03"],
+               sigs["a01"] + bytes(bad2) + sigs["a03"], sigs["a01"] + bytes(bad2) + sigs["a03"] + sigs["a04"],
+               sigs["a01"] * 3,                                   # duplicates count (F8 / Appendix C.1)
+               sigs["x99"] + sigs["u01"] + sigs["a01"] + sigs["a02"],   # non-members and unknown issuers do not count
+               sigs["x99"] + sigs["a01"] + sigs["a02"] + sigs["a04"] + sigs["x99"],
+               bytes([0xB4, 3]) + b"abc" + sigs["a01"] + sigs["a02"] + sigs["a03"]]
+    got = cs.verify_batch([tbs] * len(streams), streams, q)
+    ref = [pgp.collective_verify(env["ents"], tbs, s, oq)[0] for s in streams]
+    assert got == ref
+    assert ref == [ErrInsufficientNumberOfSignatures] * 3 + [None, ErrInsufficientNumberOfSignatures, None, None,
+                                                              ErrInsufficientNumberOfSignatures, None, None]
+    assert cs.verify(tbs, streams[3], q) == (None, True)
+    # Combine (client side, protocol/client.go:153): parse-only sufficiency of ss ++ s
+    acc_t, acc = 0, b""
+    oks = []
+    for n in ["a01", "a02", "x99", "a03"]:
+        ok, acc_t, acc = cs.combine(acc_t, acc, pk.SIGNATURE_TYPE_PGP, sigs[n], q)
+        ok_ref, _, _ = pgp.collective_combine(env["ents"], 0 if not oks else 1, acc[:-len(sigs[n])], 1, sigs[n], oq)
+        assert ok == ok_ref
+        oks.append(ok)
+    assert oks == [False, False, False, True]
+    assert cs.combine(1, b"", 2, sigs["a01"], q)[0] is False       # type mismatch
+    # Quorum predicates through the GPU tally mirror quorum.Quorum
+    assert q.is_threshold(clique[:3]) and not q.is_threshold(clique[:2]) and q.is_threshold([clique[0]] * 3)
+    assert q.is_sufficient(clique[:3]) and q.is_quorum(clique) and not q.is_quorum(clique[:3])
+    assert q.reject(clique[:2]) and not q.reject(clique[:1]) and q.get_threshold() == 3
