@@ -33,6 +33,19 @@ ITEMS = 65536
 NKEYS = 16
 
 
+def host_cores():
+    """Usable host cores: affinity mask capped by the cgroup CPU quota (containers on the GPU box
+    are quota-limited well below the 128 hardware threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -67,6 +80,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def w_pool_clean(w):
+    """The genuinely signed, known-key subset of a config-2 batch, as a pool for config 3."""
+    import numpy as np
+    keep = np.nonzero(w["expect"] == 0)[0]
+    return {"keys": w["keys"], "key_idx": w["key_idx"][keep], "sig": w["sig"][keep], "digest": w["digest"][keep]}
+
+
 def cpu_port(w, threads, reps):
     from oracle import c_oracle
     ns, es = [k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]]
@@ -82,7 +102,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from bftkv_b200 import workload
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     w = workload.make_verify_batch(ITEMS, NKEYS)
     for _ in range(args.warmup):
         cpu_port(w, threads, 1)
@@ -115,7 +135,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = workload.make_verify_batch(ITEMS, NKEYS, seed=0xBF7C0002 + rank, corrupt_seed=0xBF7C0003 + rank,
-                                   threads=max(1, (os.cpu_count() or 8) // world))
+                                   threads=max(1, host_cores() // world))
     eng = Engine(local_rank)
     eng.register_rsa_keys([k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]])
     int_peak = eng.measure_int_peak()
@@ -160,26 +180,71 @@ def run_gpu(args, rank, local_rank, world):
         assert np.array_equal(d_st[c].cpu().numpy(), w["expect"]), "device-resident results differ from expectation"
 
     # ---- end-to-end leg: pinned host buffers through the host C-ABI call ------------------------
-    h_idx = torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory()
-    h_sig = torch.from_numpy(w["sig"]).pin_memory()
-    h_dig = torch.from_numpy(w["digest"]).pin_memory()
-    h_st = torch.empty(ITEMS, dtype=torch.uint8).pin_memory()
-    for _ in range(args.warmup):
-        eng.rsa_verify_batch(h_idx, h_sig, h_dig, out=h_st)
+    # Two concurrent callers (bftkv calls the crypto layer from one goroutine per peer,
+    # transport/transport.go:110-127; the C ABI is re-entrant): while one call's kernel runs, the
+    # other call's H2D copy is in flight.  Every step still copies its full inputs H2D and its
+    # status bytes D2H inside the timed region.
+    NCALLERS = 2
+    h_in = [(torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory(), torch.from_numpy(w["sig"]).pin_memory(),
+             torch.from_numpy(w["digest"]).pin_memory(), torch.empty(ITEMS, dtype=torch.uint8).pin_memory()) for _ in range(NCALLERS)]
+    for c in range(NCALLERS):
+        for _ in range(args.warmup):
+            eng.rsa_verify_batch(h_in[c][0], h_in[c][1], h_in[c][2], out=h_in[c][3])
+
+    def caller(c, n):
+        for _ in range(n):
+            eng.rsa_verify_batch(h_in[c][0], h_in[c][1], h_in[c][2], out=h_in[c][3])
+    share = [args.steps // NCALLERS + (1 if c < args.steps % NCALLERS else 0) for c in range(NCALLERS)]
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.rsa_verify_batch(h_idx, h_sig, h_dig, out=h_st)
+    ths = [threading.Thread(target=caller, args=(c, share[c])) for c in range(NCALLERS)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    assert np.array_equal(h_st.numpy(), w["expect"]), "end-to-end results differ from expectation"
+    for c in range(NCALLERS):
+        if share[c]:
+            assert np.array_equal(h_in[c][3].numpy(), w["expect"]), "end-to-end results differ from expectation"
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- secondary: quorum-certified read ops (BASELINE configs[2]) ------------------------------
+    # 65536 read ops x 16 replicas: verify every response + wotqs read tally (K1 + K2, one stream).
+    # Signed tuples are drawn from this rank's 65536-signature pool (each slot gets a genuine
+    # signature by its replica's key; 1 M distinct signatures would take minutes to make).
+    R, M = 16, 65536
+    ro = workload.make_read_ops(w_pool_clean(w), M, R, seed=0xBF7C0004 + rank)
+    quorum = eng.quorum_create([(5, 16, 6, 11, list(range(16)))])           # n=16: f=5, READ threshold 6, suff 11
+    NQ = M * R
+    dq = {k: torch.from_numpy(v).to(dev) for k, v in [("off", ro["op_off"].astype(np.int32)), ("idx", ro["key_idx"].astype(np.int32)),
+                                                     ("sig", ro["sig"]), ("dig", ro["digest"]), ("pre", ro["pre_status"]),
+                                                     ("ts", ro["ts"].astype(np.int64)), ("val", ro["value_id"].astype(np.int32))]}
+    dq_st = torch.empty(NQ, dtype=torch.uint8, device=dev)
+    dq_bits = torch.empty(M, dtype=torch.uint8, device=dev)
+    dq_win = torch.empty(M, dtype=torch.int32, device=dev)
+
+    def qstep():
+        eng.verify_tally_batch_dev(quorum, dq["off"], dq["idx"], dq["sig"], dq["dig"], M, NQ, dq_st, dq_bits, d_pre=dq["pre"],
+                                   d_ts=dq["ts"], d_value_id=dq["val"], d_winner=dq_win, stream=stream.cuda_stream)
+    qsteps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        qstep()
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record(stream)
+    for _ in range(qsteps):
+        qstep()
+    q1.record(stream)
+    stream.synchronize()
+    barrier()
+    q_ms = q0.elapsed_time(q1)
+    assert np.array_equal(dq_st.cpu().numpy(), ro["expect_status"]), "config-3 statuses differ from expectation"
+    accepted = int((dq_win.cpu().numpy().astype(np.uint32) != 0xFFFFFFFF).sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, q_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, q_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -205,10 +270,17 @@ def run_gpu(args, rank, local_rank, world):
                    % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4"))},
         "gpu_launches": int(gpu_launches),
         "e2e": {"value": e2e_v, "unit": "verifies/s", "h2d_bytes_per_step": ITEMS * (256 + 32 + 4), "d2h_bytes_per_step": ITEMS,
-                "api": "bftq_rsa_verify_batch (host C ABI, pinned host buffers)", "ms_per_step": e2e_ms / args.steps},
-        "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE)",
+                "api": "bftq_rsa_verify_batch (host C ABI, pinned host buffers), %d concurrent callers" % NCALLERS,
+                "ms_per_step": e2e_ms / args.steps},
+        "quorum_ops": {"metric": "quorum_certified_read_ops_per_sec", "value": M * world * qsteps / (q_ms * 1e-3), "unit": "ops/s",
+                       "verifies_per_sec": NQ * world * qsteps / (q_ms * 1e-3), "steps": qsteps, "ms_per_step": q_ms / qsteps,
+                       "config": {"workload": "batch 65536 read ops x 16-replica quorum, verify + wotqs read tally (BASELINE configs[2])",
+                                  "quorum": "n=16 f=5 READ threshold 6", "accepted_ops_rank0": accepted,
+                                  "data": "synthetic; 1,048,576 tuples drawn from a pool of 65,536 genuine signatures"},
+                       "kernels_per_step": 2},
+        "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE on the FMA-heavy pipe)",
                      "frac": achieved / int_peak, "traffic": None,
-                     "peak_source": "measured live: dependency-free mad.wide.u32 micro-benchmark (bftq_measure_int_peak)",
+                     "peak_source": "measured live on this GPU: dependency-free fused IMAD.WIDE.U32 stream, 64 warps/SM (bftq_measure_int_peak)",
                      "kernel": "rsa_verify_kernel", "kernel_ms_avg": k_avg_ms, "kernel_ms_min": kernel_ms[0],
                      "algorithmic_macs_per_verify": MACS_PER_VERIFY,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
@@ -216,7 +288,7 @@ def run_gpu(args, rank, local_rank, world):
         "clocks": clocks,
     }
     if world == 1:
-        threads = os.cpu_count() or 1
+        threads = host_cores()
         reps = 8
         rate, st = cpu_port(w, threads, reps)
         assert (st == w["expect"]).all()
