@@ -3,6 +3,7 @@
 // pinned staging.  No CPU verification path exists here on purpose.
 #include "../../include/bftq.h"
 #include "rsa_verify.cuh"
+#include "rsa_verify_r32.cuh"
 #include "tally.cuh"
 #include "lagrange.cuh"
 #include "pgp_digest.cuh"
@@ -95,6 +96,10 @@ struct bftq_engine {
   std::vector<bftq::RsaKeyDev> h_keys;
   bftq::RsaKeyDev* d_keys = nullptr;
   size_t d_keys_cap = 0;
+  std::vector<bftq::r32::RsaKey32> h_keys32;     // radix-2^32 constants of the same keys
+  bftq::r32::RsaKey32* d_keys32 = nullptr;
+  bool all_2048 = true;                          // every registered modulus has exactly 2048 bits
+  int rsa_kernel = 0;                            // 0 auto, 28 force radix-2^28, 32 force radix-2^32 (env BFTQ_RSA_KERNEL)
   std::vector<StagingSlot*> slots;
   bftq_stats_t stats{};
   std::map<std::string, uint32_t> key_lookup;   // (modulus bytes || e) -> key table index
@@ -227,6 +232,20 @@ int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_s
     e->stats.launches += 1;
     e->stats.items += n_items;
   }
+  const bool use32 = e->rsa_kernel == 32 || (e->rsa_kernel == 0 && e->all_2048);
+  if (use32) {
+    if (!e->all_2048) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a registered modulus is not 2048 bits");
+    auto kern = bftq::r32::rsa_verify_r32_kernel<128, 4>;
+    static thread_local int occ32 = 0;
+    if (!occ32) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, kern, 128, 0)); if (occ32 < 1) occ32 = 1; }
+    const uint64_t per_block = 4 * 8;
+    uint64_t grid = std::min<uint64_t>((n_items + per_block - 1) / per_block, (uint64_t)e->sm_count * occ32);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 128, 0, st>>>(e->d_keys32, (uint32_t)e->h_keys32.size(), d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
+                                         d_pre, d_status);
+    CU(cudaGetLastError());
+    return BFTQ_OK;
+  }
   switch (e->rsa_t) {
     case 8: return launch_rsa<8, 10, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
     default: return launch_rsa<4, 19, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
@@ -279,6 +298,10 @@ int bftq_init(int device, bftq_engine** out) {
   auto* e = new bftq_engine();
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
+  if (const char* k = getenv("BFTQ_RSA_KERNEL")) {
+    if (!strcmp(k, "r28")) e->rsa_kernel = 28;
+    if (!strcmp(k, "r32")) e->rsa_kernel = 32;
+  }
   if (const char* t = getenv("BFTQ_RSA_T")) {
     int v = atoi(t);
     if (v == 4 || v == 8) e->rsa_t = v;
@@ -297,6 +320,7 @@ void bftq_shutdown(bftq_engine* e) {
     delete s;
   }
   if (e->d_keys) cudaFree(e->d_keys);
+  if (e->d_keys32) cudaFree(e->d_keys32);
   delete e;
 }
 
@@ -311,6 +335,8 @@ int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* 
                            uint32_t* first_index) {
   if (!e || !n_be || !exps) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::vector<bftq::RsaKeyDev> fresh(count);
+  std::vector<bftq::r32::RsaKey32> fresh32(count);
+  bool fresh_all_2048 = true;
   for (uint32_t k = 0; k < count; k++) {
     U2048 n;
     from_be(n, n_be + (size_t)k * 256);
@@ -339,23 +365,47 @@ int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* 
       while (exp2 < target) { dbl_mod(x, n); exp2++; }
       to_digits(x, kd.r2[layout], bftq::kMaxDigits);
     }
+    // radix-2^32 constants: n, R^2 = 2^4096 mod n, -n^-1 mod 2^32
+    bftq::r32::RsaKey32& k32 = fresh32[k];
+    memset(&k32, 0, sizeof(k32));
+    for (int i = 0; i < 32; i++) { k32.n[2 * i] = (uint32_t)n.w[i]; k32.n[2 * i + 1] = (uint32_t)(n.w[i] >> 32); }
+    k32.n0inv = 0u - inv;
+    k32.e = exps[k];
+    k32.nbits = (uint32_t)nb;
+    {
+      U2048 y;
+      memset(&y, 0, sizeof(y));
+      y.w[31] = 1ull << 63;
+      while (ge(y, n)) sub(y, n);
+      for (int ex = 2047; ex < 4096; ex++) dbl_mod(y, n);
+      for (int i = 0; i < 32; i++) { k32.r2[2 * i] = (uint32_t)y.w[i]; k32.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
+    }
+    if (nb != 2048) fresh_all_2048 = false;
   }
   std::lock_guard<std::mutex> g(e->mu);
   CU(cudaSetDevice(e->device));
   const size_t old = e->h_keys.size();
   e->h_keys.insert(e->h_keys.end(), fresh.begin(), fresh.end());
+  e->h_keys32.insert(e->h_keys32.end(), fresh32.begin(), fresh32.end());
+  e->all_2048 = e->all_2048 && fresh_all_2048;
   if (e->h_keys.size() > e->d_keys_cap) {
     // Kernels in flight may still read the old table: synchronise before replacing it.
     CU(cudaDeviceSynchronize());
     size_t cap = std::max<size_t>(64, e->h_keys.size() * 2);
     bftq::RsaKeyDev* nd = nullptr;
+    bftq::r32::RsaKey32* nd32 = nullptr;
     CU(cudaMalloc((void**)&nd, cap * sizeof(bftq::RsaKeyDev)));
+    CU(cudaMalloc((void**)&nd32, cap * sizeof(bftq::r32::RsaKey32)));
     if (e->d_keys) cudaFree(e->d_keys);
+    if (e->d_keys32) cudaFree(e->d_keys32);
     e->d_keys = nd;
+    e->d_keys32 = nd32;
     e->d_keys_cap = cap;
     CU(cudaMemcpy(e->d_keys, e->h_keys.data(), e->h_keys.size() * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_keys32, e->h_keys32.data(), e->h_keys32.size() * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice));
   } else {
     CU(cudaMemcpy(e->d_keys + old, e->h_keys.data() + old, count * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_keys32 + old, e->h_keys32.data() + old, count * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice));
   }
   if (first_index) *first_index = (uint32_t)old;
   return BFTQ_OK;
