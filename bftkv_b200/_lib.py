@@ -61,6 +61,13 @@ def load():
         "bftq_signature_signers": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u32p]),
         "bftq_collective_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_collective_combine_sufficient": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_int32)]),
+        "bftq_graph_create": (C.c_int, [C.POINTER(vp)]),
+        "bftq_graph_destroy": (None, [vp]),
+        "bftq_graph_add_node": (C.c_int, [vp, C.c_uint64, vp, C.c_uint32]),
+        "bftq_graph_set_self": (C.c_int, [vp, C.c_uint64]),
+        "bftq_graph_remove_node": (C.c_int, [vp, C.c_uint64]),
+        "bftq_graph_revoke": (C.c_int, [vp, C.c_uint64]),
+        "bftq_graph_choose_quorum": (C.c_int, [vp, C.c_int, vp, C.c_uint32, u32p, vp, C.c_uint32, u32p]),
         "bftq_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "bftq_measure_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
     }

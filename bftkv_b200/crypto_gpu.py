@@ -191,3 +191,49 @@ class CollectiveSignature:
 
     def signers(self, ss_data: bytes) -> List[int]:
         return self.signature.signers(ss_data)
+
+
+READ, WRITE, AUTH, CERT, PEER = 0x01, 0x02, 0x04, 0x08, 0x10     # quorum/quorum.go:10-16
+
+
+class QuorumSystem:
+    """quorum.QuorumSystem (quorum/quorum.go:27-29) over the trust graph: mirrors graph.AddNodes /
+    SetSelfNodes / RemoveNodes / Revoke (node/graph/graph.go) and wotqs.ChooseQuorum.  Host only."""
+
+    def __init__(self):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.bftq_graph_create(C.byref(h)))
+        self._h = h
+
+    def add_node(self, node_id: int, signers: Sequence[int] = ()):
+        a = np.asarray(list(signers) or [0], np.uint64)
+        _lib.check(self._lib.bftq_graph_add_node(self._h, node_id, C.c_void_p(a.ctypes.data), len(signers)))
+
+    def set_self(self, node_id: int):
+        _lib.check(self._lib.bftq_graph_set_self(self._h, node_id))
+
+    def remove_node(self, node_id: int):
+        _lib.check(self._lib.bftq_graph_remove_node(self._h, node_id))
+
+    def revoke(self, node_id: int):
+        _lib.check(self._lib.bftq_graph_revoke(self._h, node_id))
+
+    def choose_quorum_desc(self, rw: int):
+        """wotqs.ChooseQuorum(rw) as a descriptor: list of (f, min, threshold, suff, [node ids])."""
+        nq, nm = C.c_uint32(), C.c_uint32()
+        _lib.check(self._lib.bftq_graph_choose_quorum(self._h, rw, None, 0, C.byref(nq), None, 0, C.byref(nm)))
+        arr = (QCIds * max(1, nq.value))()
+        mem = np.zeros(max(1, nm.value), np.uint64)
+        _lib.check(self._lib.bftq_graph_choose_quorum(self._h, rw, C.cast(arr, C.c_void_p), nq.value, C.byref(nq),
+                                                      C.c_void_p(mem.ctypes.data), nm.value, C.byref(nm)))
+        return [(arr[i].f, arr[i].min, arr[i].threshold, arr[i].suff,
+                 [int(x) for x in mem[arr[i].member_off:arr[i].member_off + arr[i].member_cnt]]) for i in range(nq.value)]
+
+    def choose_quorum(self, rw: int, engine: Engine) -> Quorum:
+        return Quorum(engine, self.choose_quorum_desc(rw))
+
+    def close(self):
+        if self._h:
+            self._lib.bftq_graph_destroy(self._h)
+            self._h = None

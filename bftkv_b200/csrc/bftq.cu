@@ -8,6 +8,7 @@
 #include "lagrange.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_host.hpp"
+#include "wotqs_host.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -1126,6 +1127,58 @@ int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qc
   rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
   if (rc) return rc;
   *out = (bits[0] & BFTQ_TALLY_IS_SUFFICIENT) ? 1 : 0;
+  return BFTQ_OK;
+}
+
+// ---- quorum-descriptor builder ------------------------------------------------------------------
+}  // extern "C"
+struct bftq_graph { std::mutex mu; bftq::wot::Graph g; };
+extern "C" {
+int bftq_graph_create(bftq_graph** out) {
+  if (!out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  *out = new bftq_graph();
+  return BFTQ_OK;
+}
+void bftq_graph_destroy(bftq_graph* g) { delete g; }
+int bftq_graph_add_node(bftq_graph* g, uint64_t id, const uint64_t* signer_ids, uint32_t n_signers) {
+  if (!g || (n_signers && !signer_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(g->mu);
+  g->g.add_node(id, signer_ids, n_signers);
+  return BFTQ_OK;
+}
+int bftq_graph_set_self(bftq_graph* g, uint64_t id) {
+  if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(g->mu);
+  g->g.set_self(id);
+  return BFTQ_OK;
+}
+int bftq_graph_remove_node(bftq_graph* g, uint64_t id) {
+  if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(g->mu);
+  g->g.remove_node(id);
+  return BFTQ_OK;
+}
+int bftq_graph_revoke(bftq_graph* g, uint64_t id) {
+  if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(g->mu);
+  g->g.revoke(id);
+  return BFTQ_OK;
+}
+int bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint32_t cap_qc, uint32_t* n_qc, uint64_t* out_members,
+                             uint32_t cap_members, uint32_t* n_members) {
+  if (!g || !n_qc || !n_members) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<bftq::wot::QC> qcs;
+  {
+    std::lock_guard<std::mutex> l(g->mu);
+    g->g.choose_quorum(rw, qcs);
+  }
+  uint32_t off = 0;
+  for (size_t c = 0; c < qcs.size(); c++) {
+    if (out_qcs && c < cap_qc) out_qcs[c] = bftq_qc_ids_t{qcs[c].f, qcs[c].min, qcs[c].threshold, qcs[c].suff, off, (uint32_t)qcs[c].nodes.size()};
+    for (uint64_t id : qcs[c].nodes) { if (out_members && off < cap_members) out_members[off] = id; off++; }
+  }
+  *n_qc = (uint32_t)qcs.size();
+  *n_members = off;
   return BFTQ_OK;
 }
 

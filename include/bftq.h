@@ -248,6 +248,30 @@ int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uin
 int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
                                        uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out);
 
+/* ---- quorum-descriptor builder (host only; no GPU needed) --------------------------------------
+ * The step before the tally: wotqs.ChooseQuorum over the PGP trust graph
+ * (quorum/wotqs/wotqs.go:36-127, node/graph/graph.go:46-75,117-125,279-393,420-438).  The shim
+ * mirrors graph.AddNodes / SetSelfNodes / RemoveNodes / Revoke into it (node ids + the issuer ids of
+ * each node's certifications, crypto_pgp.go:80-88 = bftq_keyring_certifiers) and caches the
+ * descriptor per (rw, graph version) instead of recomputing it on every call as the reference
+ * does.  rw = OR of BFTQ_RW_* (quorum/quorum.go:10-16). */
+#define BFTQ_RW_READ  0x01
+#define BFTQ_RW_WRITE 0x02
+#define BFTQ_RW_AUTH  0x04
+#define BFTQ_RW_CERT  0x08
+#define BFTQ_RW_PEER  0x10
+typedef struct bftq_graph bftq_graph;
+int  bftq_graph_create(bftq_graph** out);
+void bftq_graph_destroy(bftq_graph* g);
+int  bftq_graph_add_node(bftq_graph* g, uint64_t id, const uint64_t* signer_ids, uint32_t n_signers);   /* graph.go:46-75 */
+int  bftq_graph_set_self(bftq_graph* g, uint64_t id);                                                   /* graph.go:77-88 */
+int  bftq_graph_remove_node(bftq_graph* g, uint64_t id);                                                /* graph.go:90-108 */
+int  bftq_graph_revoke(bftq_graph* g, uint64_t id);                                                     /* graph.go:131-140 */
+/* wotqs.ChooseQuorum(rw): writes up to cap_qc cliques and cap_members member ids; *n_qc / *n_members
+ * receive the required counts (call with caps 0 to size the buffers). */
+int  bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint32_t cap_qc, uint32_t* n_qc,
+                              uint64_t* out_members, uint32_t cap_members, uint32_t* n_members);
+
 /* ---- statistics ------------------------------------------------------------------------------
  * Counters since bftq_init (SURVEY §5 "metrics"): items verified, kernel launches. */
 typedef struct {
