@@ -39,6 +39,9 @@ def load():
         "bftq_device_sm_count": (C.c_int, [vp]),
         "bftq_key_count": (C.c_int, [vp]),
         "bftq_register_rsa_keys": (C.c_int, [vp, vp, vp, C.c_uint32, u32p]),
+        "bftq_register_rsa_keys_k": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, u32p]),
+        "bftq_rsa_verify_batch_k": (C.c_int, [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp]),
+        "bftq_rsa_verify_batch_dev_k": (C.c_int, [vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]),
         "bftq_rsa_verify_batch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp]),
         "bftq_rsa_verify_batch_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp]),
         "bftq_quorum_create": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(vp)]),

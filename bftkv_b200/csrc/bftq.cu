@@ -34,47 +34,48 @@ int fail(int code, const std::string& msg) {
       return fail(BFTQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
   } while (0)
 
-// ---- tiny host big-number helpers (2048-bit, 32 x u64 limbs, little-endian) -------------------
-struct U2048 { uint64_t w[32]; };
+// ---- tiny host big-number helpers (up to 4096 bit, 64 x u64 limbs, little-endian) ---------------
+constexpr int kHL = 64;
+struct UBig { uint64_t w[kHL]; };
 
-bool ge(const U2048& a, const U2048& b) {
-  for (int i = 31; i >= 0; i--) { if (a.w[i] != b.w[i]) return a.w[i] > b.w[i]; }
+bool ge(const UBig& a, const UBig& b) {
+  for (int i = kHL - 1; i >= 0; i--) { if (a.w[i] != b.w[i]) return a.w[i] > b.w[i]; }
   return true;
 }
-void sub(U2048& a, const U2048& b) {
+void sub(UBig& a, const UBig& b) {
   unsigned __int128 br = 0;
-  for (int i = 0; i < 32; i++) {
+  for (int i = 0; i < kHL; i++) {
     unsigned __int128 d = (unsigned __int128)a.w[i] - b.w[i] - (uint64_t)br;
     a.w[i] = (uint64_t)d;
     br = (d >> 64) & 1;
   }
 }
 // a = 2a mod n   (a < n on entry)
-void dbl_mod(U2048& a, const U2048& n) {
-  uint64_t top = a.w[31] >> 63;
-  for (int i = 31; i > 0; i--) a.w[i] = (a.w[i] << 1) | (a.w[i - 1] >> 63);
+void dbl_mod(UBig& a, const UBig& n) {
+  uint64_t top = a.w[kHL - 1] >> 63;
+  for (int i = kHL - 1; i > 0; i--) a.w[i] = (a.w[i] << 1) | (a.w[i - 1] >> 63);
   a.w[0] <<= 1;
   if (top || ge(a, n)) sub(a, n);
 }
-int bitlen(const U2048& a) {
-  for (int i = 31; i >= 0; i--) if (a.w[i]) return 64 * i + 64 - __builtin_clzll(a.w[i]);
+int bitlen(const UBig& a) {
+  for (int i = kHL - 1; i >= 0; i--) if (a.w[i]) return 64 * i + 64 - __builtin_clzll(a.w[i]);
   return 0;
 }
-void from_be(U2048& a, const uint8_t* be) {   // 256 bytes big-endian
-  for (int i = 0; i < 32; i++) {
-    uint64_t v = 0;
-    for (int b = 0; b < 8; b++) v = (v << 8) | be[256 - 8 * (i + 1) + b];
-    a.w[i] = v;
+void from_be(UBig& a, const uint8_t* be, size_t len) {   // len bytes big-endian, len <= 512
+  memset(&a, 0, sizeof(a));
+  for (size_t i = 0; i < len; i++) {
+    const size_t bi = len - 1 - i;                        // little-endian byte number
+    a.w[bi >> 3] |= (uint64_t)be[i] << (8 * (bi & 7));
   }
 }
-void to_digits(const U2048& a, uint32_t* d, int nd) {
+void to_digits(const UBig& a, uint32_t* d, int nd) {
   for (int i = 0; i < nd; i++) {
     int o = 28 * i;
     uint32_t v = 0;
-    if (o < 2048) {
+    if (o < 64 * kHL) {
       int wi = o >> 6, sh = o & 63;
       unsigned __int128 t = a.w[wi];
-      if (wi + 1 < 32) t |= (unsigned __int128)a.w[wi + 1] << 64;
+      if (wi + 1 < kHL) t |= (unsigned __int128)a.w[wi + 1] << 64;
       v = (uint32_t)(t >> sh) & bftq::kDigitMask;
     }
     d[i] = v;
@@ -205,10 +206,10 @@ class Arena {
   size_t total_ = 0;
 };
 
-template <int T, int W, int BLOCK>
+template <int T, int W, int BLOCK, int KB>
 int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
                uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st) {
-  auto kern = bftq::rsa_verify_kernel<T, W, BLOCK>;
+  auto kern = bftq::rsa_verify_kernel<T, W, BLOCK, KB>;
   static thread_local int occ_cache = 0;
   int occ = occ_cache;
   if (!occ) {
@@ -227,13 +228,14 @@ int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, 
 }
 
 int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
-                   uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st) {
+                   uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st,
+                   int kb = 256) {
   {
     std::lock_guard<std::mutex> g(e->mu);
     e->stats.launches += 1;
     e->stats.items += n_items;
   }
-  const bool use32 = e->rsa_kernel == 32 || (e->rsa_kernel == 0 && e->all_2048);
+  const bool use32 = kb == 256 && (e->rsa_kernel == 32 || (e->rsa_kernel == 0 && e->all_2048));
   if (use32) {
     if (!e->all_2048) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a registered modulus is not 2048 bits");
     auto kern = bftq::r32::rsa_verify_r32_kernel<128, 4>;
@@ -247,10 +249,16 @@ int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_s
     CU(cudaGetLastError());
     return BFTQ_OK;
   }
-  switch (e->rsa_t) {
-    case 8: return launch_rsa<8, 10, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
-    default: return launch_rsa<4, 19, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+  switch (kb) {
+    case 128: return launch_rsa<4, 10, 128, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 192: return launch_rsa<4, 14, 128, 192>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 384: return launch_rsa<8, 14, 128, 384>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 512: return launch_rsa<8, 19, 128, 512>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 256: break;
+    default: return fail(BFTQ_ERR_UNSUPPORTED_KEY, "key size class not built (128/192/256/384/512 bytes are)");
   }
+  if (e->rsa_t == 8) return launch_rsa<8, 10, 128, 256>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+  return launch_rsa<4, 19, 128, 256>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
 }
 
 // ---- integer-pipe peak micro-benchmark ---------------------------------------------------------
@@ -334,54 +342,60 @@ int bftq_key_count(bftq_engine* e) {
 
 int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* exps, uint32_t count,
                            uint32_t* first_index) {
+  return bftq_register_rsa_keys_k(e, n_be, 256, exps, count, first_index);
+}
+
+int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t stride, const uint32_t* exps, uint32_t count,
+                             uint32_t* first_index) {
   if (!e || !n_be || !exps) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (stride == 0 || stride > 512) return fail(BFTQ_ERR_INVALID_ARG, "modulus stride must be 1..512 bytes");
   std::vector<bftq::RsaKeyDev> fresh(count);
   std::vector<bftq::r32::RsaKey32> fresh32(count);
   bool fresh_all_2048 = true;
   for (uint32_t k = 0; k < count; k++) {
-    U2048 n;
-    from_be(n, n_be + (size_t)k * 256);
+    UBig n;
+    from_be(n, n_be + (size_t)k * stride, stride);
     const int nb = bitlen(n);
-    if (nb < 2041 || nb > 2048 || !(n.w[0] & 1))
-      return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd and 2041..2048 bits (key " + std::to_string(k) + ")");
+    const int kb = (nb + 7) / 8;
+    if (!bftq::class_supported(kb) || !(n.w[0] & 1))
+      return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd with ceil(bits/8) in {128,192,256,384,512} (key " + std::to_string(k) + ")");
     if (exps[k] == 0) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "public exponent 0");
     bftq::RsaKeyDev& kd = fresh[k];
     memset(&kd, 0, sizeof(kd));
     to_digits(n, kd.n, bftq::kMaxDigits);
-    // -n^-1 mod 2^28 by Newton iteration on the low word.
+    // -n^-1 mod 2^32 by Newton iteration on the low word (masked to 28 bits for the digit kernels).
     uint32_t n0 = (uint32_t)n.w[0], inv = n0;
     for (int i = 0; i < 5; i++) inv *= 2u - n0 * inv;
     kd.n0inv = (0u - inv) & bftq::kDigitMask;
     kd.e = exps[k];
     kd.nbits = (uint32_t)nb;
-    // R^2 mod n for each digit layout: start from 2^2047 mod n and keep doubling.
-    U2048 x;
+    kd.kbytes = (uint32_t)kb;
+    // R^2 mod n for each digit layout of the class: 2^(2*28*digits) by repeated doubling from 1.
+    UBig x;
     memset(&x, 0, sizeof(x));
-    x.w[31] = 1ull << 63;                    // 2^2047
-    if (ge(x, n)) sub(x, n);                 // n >= 2^2040 so one subtraction may not suffice...
-    while (ge(x, n)) sub(x, n);
-    int exp2 = 2047;
+    x.w[0] = 1;
+    int exp2 = 0;
     for (int layout = 0; layout < bftq::kNumLayouts; layout++) {
-      const int target = 2 * 28 * bftq::layout_digits(layout);
+      const int digits = bftq::class_digits(kb, layout == 1 && kb != 256 ? 0 : layout);
+      const int target = 2 * 28 * digits;
       while (exp2 < target) { dbl_mod(x, n); exp2++; }
-      to_digits(x, kd.r2[layout], bftq::kMaxDigits);
+      if (exp2 == target) to_digits(x, kd.r2[layout], bftq::kMaxDigits);
     }
-    // radix-2^32 constants: n, R^2 = 2^4096 mod n, -n^-1 mod 2^32
+    // radix-2^32 constants (fast path, meaningful for exactly-2048-bit moduli): n, 2^4096 mod n, -n^-1 mod 2^32
     bftq::r32::RsaKey32& k32 = fresh32[k];
     memset(&k32, 0, sizeof(k32));
     for (int i = 0; i < 32; i++) { k32.n[2 * i] = (uint32_t)n.w[i]; k32.n[2 * i + 1] = (uint32_t)(n.w[i] >> 32); }
     k32.n0inv = 0u - inv;
     k32.e = exps[k];
     k32.nbits = (uint32_t)nb;
-    {
-      U2048 y;
+    if (nb == 2048) {
+      UBig y;
       memset(&y, 0, sizeof(y));
-      y.w[31] = 1ull << 63;
-      while (ge(y, n)) sub(y, n);
-      for (int ex = 2047; ex < 4096; ex++) dbl_mod(y, n);
+      y.w[0] = 1;
+      for (int ex = 0; ex < 4096; ex++) dbl_mod(y, n);
       for (int i = 0; i < 32; i++) { k32.r2[2 * i] = (uint32_t)y.w[i]; k32.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
     }
-    if (nb != 2048) fresh_all_2048 = false;
+    if (kb == 256 && nb != 2048) fresh_all_2048 = false;
   }
   std::lock_guard<std::mutex> g(e->mu);
   CU(cudaSetDevice(e->device));
@@ -415,30 +429,43 @@ int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* 
 int bftq_rsa_verify_batch_dev(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig_be,
                               const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
                               uint8_t* d_status, void* cuda_stream) {
+  return bftq_rsa_verify_batch_dev_k(e, 256, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_status, cuda_stream);
+}
+
+int bftq_rsa_verify_batch_dev_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* d_key_idx, const uint8_t* d_sig_be,
+                                const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
+                                uint8_t* d_status, void* cuda_stream) {
+  if (!bftq::class_supported((int)key_bytes)) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "key size class not built");
   if (!e || !d_key_idx || !d_sig_be || !d_digest || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (bftq::host_hash_dlen(hash_alg) == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_items == 0) return BFTQ_OK;
   if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   CU(cudaSetDevice(e->device));
-  return launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, nullptr, d_status, (cudaStream_t)cuda_stream);
+  return launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, nullptr, d_status, (cudaStream_t)cuda_stream, (int)key_bytes);
 }
 
 int bftq_rsa_verify_batch(bftq_engine* e, const uint32_t* key_idx, const uint8_t* sig_be, const uint8_t* digest,
                           uint32_t hash_alg, uint64_t n_items, uint32_t flags, uint8_t* out_status) {
+  return bftq_rsa_verify_batch_k(e, 256, key_idx, sig_be, digest, hash_alg, n_items, flags, out_status);
+}
+
+int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* key_idx, const uint8_t* sig_be, const uint8_t* digest,
+                            uint32_t hash_alg, uint64_t n_items, uint32_t flags, uint8_t* out_status) {
   if (!e || !key_idx || !sig_be || !digest || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!bftq::class_supported((int)key_bytes)) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "key size class not built");
   const int dlen = bftq::host_hash_dlen(hash_alg);
   if (dlen == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_items == 0) return BFTQ_OK;
   if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   Arena a(e);
   uint8_t *d_sig, *d_dig, *d_st; uint32_t* d_idx;
-  a.in(&d_sig, sig_be, (size_t)n_items * 256);
+  a.in(&d_sig, sig_be, (size_t)n_items * key_bytes);
   a.in(&d_dig, digest, (size_t)n_items * dlen);
   a.in(&d_idx, key_idx, (size_t)n_items);
   a.out(&d_st, out_status, (size_t)n_items);
   int rc = a.upload();
   if (rc) return rc;
-  rc = launch_rsa_any(e, d_idx, d_sig, d_dig, hash_alg, n_items, flags, nullptr, d_st, a.stream());
+  rc = launch_rsa_any(e, d_idx, d_sig, d_dig, hash_alg, n_items, flags, nullptr, d_st, a.stream(), (int)key_bytes);
   if (rc) return rc;
   return a.download();
 }
@@ -722,7 +749,7 @@ namespace pg = bftq::pgp;
 // Enter an RSA key in the engine's table (deduplicated).  Returns -1 when the size is not built.
 int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
   if (!(k.algo == 1 || k.algo == 2 || k.algo == 3)) return -1;
-  if (k.nbits < 2041 || k.nbits > 2048 || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
+  if (!bftq::class_supported((int)(k.nbits + 7) / 8) || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
   std::string id((const char*)k.n_be.data(), k.n_be.size());
   id.append((const char*)&k.e, 4);
   {
@@ -730,11 +757,11 @@ int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
     auto it = e->key_lookup.find(id);
     if (it != e->key_lookup.end()) return (int32_t)it->second;
   }
-  uint8_t n_be[256];
-  memset(n_be, 0, 256);
-  memcpy(n_be + 256 - k.n_be.size(), k.n_be.data(), k.n_be.size());
+  uint8_t n_be[512];
+  memset(n_be, 0, 512);
+  memcpy(n_be + 512 - k.n_be.size(), k.n_be.data(), k.n_be.size());
   uint32_t first = 0;
-  if (bftq_register_rsa_keys(e, n_be, &k.e, 1, &first) != BFTQ_OK) return -1;
+  if (bftq_register_rsa_keys_k(e, n_be, 512, &k.e, 1, &first) != BFTQ_OK) return -1;
   std::lock_guard<std::mutex> g(e->mu);
   e->key_lookup[id] = first;
   return (int32_t)first;
@@ -750,10 +777,11 @@ struct Tuple {
   uint64_t signer_id;          // primary key id of the candidate key's entity
   uint8_t pre;                 // status decided on the host (0 = ask the GPU)
   uint8_t hash_id;
+  uint16_t kbytes;             // key-size class of the candidate key (signature is padded to it)
   uint16_t tag;
   uint32_t data_idx;
   uint32_t suffix_pos, suffix_len;   // into suffix blob
-  uint8_t sig[256];
+  uint8_t sig[512];
 };
 struct Plan {
   std::vector<Tuple> tuples;
@@ -806,7 +834,6 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
       } else if (sp.sig_type != 0x00) common_pre = BFTQ_ST_BAD_SIGNATURE;       // hashForSignature: unsupported type
       if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3)) common_pre = BFTQ_ST_UNSUPPORTED;   // DSA / ECDSA: not built
       if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // MD5 / RIPEMD-160: not built
-      if (!common_pre && sp.mpi.size() > 256) common_pre = BFTQ_ST_BAD_SIGNATURE;                    // len(sig) != k
       for (const pg::KeyRef& kr : keys) {
         Tuple t;
         memset(&t, 0, sizeof(t));
@@ -819,7 +846,10 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
         if (!t.pre && kr.key->algo != sp.pk_algo) t.pre = BFTQ_ST_BAD_SIGNATURE;   // "different algorithms"
         if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
         if (t.key_idx < 0) t.key_idx = 0;
-        if (sp.mpi.size() <= 256) memcpy(t.sig + 256 - sp.mpi.size(), sp.mpi.data(), sp.mpi.size());   // padToKeySize
+        const size_t kb = (kr.key->nbits + 7) / 8;                                  // pub.Size()
+        t.kbytes = (uint16_t)(bftq::class_supported((int)kb) ? kb : 256);
+        if (sp.mpi.size() <= t.kbytes) memcpy(t.sig + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size());   // padToKeySize
+        else if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE;                             // len(sig) != k
         pl.tuples.push_back(t);
       }
       calls++;
@@ -836,18 +866,18 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
 
 // digest (K4) -> tag check -> RSA verify (K1) for every tuple of the plan; tuples are grouped by hash
 // algorithm (digest length differs), each group is one K4 + one K1 launch on one stream.
-int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, std::vector<uint8_t>& status) {
+int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, int kb, std::vector<uint8_t>& status) {
   const size_t nt = sel.size();
   const int dlen = bftq::host_hash_dlen(hash_alg);
   std::vector<uint32_t> key_idx(nt), data_idx(nt);
   std::vector<uint16_t> tags(nt);
-  std::vector<uint8_t> pre(nt), sigs(nt * 256), st(nt);
+  std::vector<uint8_t> pre(nt), sigs(nt * (size_t)kb), st(nt);
   std::vector<uint64_t> soff(nt + 1);
   std::vector<uint8_t> sblob;
   for (size_t i = 0; i < nt; i++) {
     const Tuple& t = pl.tuples[sel[i]];
     key_idx[i] = (uint32_t)t.key_idx; data_idx[i] = t.data_idx; tags[i] = t.tag; pre[i] = t.pre;
-    memcpy(&sigs[i * 256], t.sig, 256);
+    memcpy(&sigs[i * (size_t)kb], t.sig, kb);
     soff[i] = sblob.size();
     sblob.insert(sblob.end(), pl.suffix_blob.begin() + t.suffix_pos, pl.suffix_blob.begin() + t.suffix_pos + t.suffix_len);
   }
@@ -866,14 +896,14 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
   a.in(&d_kidx, key_idx.data(), nt);
   a.in(&d_tags, tags.data(), nt);
   a.in(&d_pre, pre.data(), nt);
-  a.in(&d_sig, sigs.data(), nt * 256);
+  a.in(&d_sig, sigs.data(), nt * (size_t)kb);
   a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
   a.out(&d_st, st.data(), nt);
   int rc = a.upload();
   if (rc) return rc;
   CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, nt, d_dig, d_tags, d_pre, a.stream()));
   { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
-  rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream());
+  rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream(), kb);
   if (rc) return rc;
   rc = a.download();
   if (rc) return rc;
@@ -883,10 +913,10 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
 
 int run_plan(bftq_engine* e, Plan& pl, std::vector<uint8_t>& status) {
   status.assign(pl.tuples.size(), 0);
-  std::map<uint32_t, std::vector<uint32_t>> groups;
-  for (size_t i = 0; i < pl.tuples.size(); i++) groups[pl.tuples[i].hash_id].push_back((uint32_t)i);
+  std::map<std::pair<uint32_t, int>, std::vector<uint32_t>> groups;    // (hash algorithm, key-size class)
+  for (size_t i = 0; i < pl.tuples.size(); i++) groups[{pl.tuples[i].hash_id, (int)pl.tuples[i].kbytes}].push_back((uint32_t)i);
   for (auto& g : groups) {
-    int rc = run_plan_group(e, pl, g.second, g.first, status);
+    int rc = run_plan_group(e, pl, g.second, g.first.first, g.first.second, status);
     if (rc) return rc;
   }
   return BFTQ_OK;

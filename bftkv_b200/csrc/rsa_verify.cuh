@@ -26,21 +26,28 @@ namespace bftq {
 
 constexpr int kDigitBits = 28;
 constexpr uint32_t kDigitMask = (1u << kDigitBits) - 1u;
-constexpr int kRsaBytes = 256;       // k = 256: RSA-2048
+constexpr int kRsaBytes = 256;       // k = 256: RSA-2048 (the class the fast path and the flat API default to)
 constexpr int kRsaWords = 64;
-constexpr int kMaxDigits = 80;       // digits kept per key (T*W <= 80)
-constexpr int kNumLayouts = 3;       // R depends on the digit count: 74 (T=2), 76 (T=4), 80 (T=8)
+constexpr int kMaxDigits = 152;      // digits kept per key (4096-bit class: 8 lanes x 19)
+constexpr int kNumLayouts = 2;       // layout 0 = the class's default (T,W), layout 1 = alternative (2048-bit class only)
 
-__host__ __device__ constexpr int layout_digits(int layout) { return layout == 0 ? 74 : (layout == 1 ? 76 : 80); }
+// Key-size classes: k = modulus bytes (what Go's pub.Size() returns).  Digit layout per class:
+//   k=128 (1024 bit): 4 lanes x 10 digits    k=192 (1536): 4 x 14    k=256 (2048): 4 x 19 [alt 8 x 10]
+//   k=384 (3072 bit): 8 lanes x 14 digits    k=512 (4096): 8 x 19
+// T*W*28 >= 8k + 24 always, so R > 2^24 n and Montgomery products never need a conditional subtraction.
+__host__ __device__ constexpr int class_digits(int kb, int layout) {
+  return kb == 128 ? 40 : kb == 192 ? 56 : kb == 256 ? (layout == 0 ? 76 : 80) : kb == 384 ? 112 : kb == 512 ? 152 : 0;
+}
+__host__ inline bool class_supported(int kb) { return kb == 128 || kb == 192 || kb == 256 || kb == 384 || kb == 512; }
 
 // Per-key constants, precomputed on the host at bftq_register_rsa_keys().
 struct RsaKeyDev {
   uint32_t n[kMaxDigits];                 // modulus, radix 2^28, little-endian digits, zero padded
-  uint32_t r2[kNumLayouts][kMaxDigits];   // R^2 mod n for R = 2^(28*digits(layout))
+  uint32_t r2[kNumLayouts][kMaxDigits];   // R^2 mod n for R = 2^(28*class_digits(kbytes, layout))
   uint32_t n0inv;                         // -n^-1 mod 2^28
   uint32_t e;                             // public exponent (>= 1)
   uint32_t nbits;
-  uint32_t pad;
+  uint32_t kbytes;                        // key-size class = ceil(nbits / 8)
 };
 
 // DigestInfo prefixes, identical to Go's crypto/rsa hashPrefixes (and to the copy in the
@@ -66,18 +73,20 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---- little helpers --------------------------------------------------------------------------
 
-// 32-bit little-endian word k of a 256-byte big-endian integer in global memory.
+// 32-bit little-endian word k of a KB-byte big-endian integer in global memory.
+template <int KB = kRsaBytes>
 __device__ __forceinline__ uint32_t be_word(const uint8_t* p, int k) {
-  if (k >= kRsaWords) return 0u;
-  uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p + (kRsaBytes - 4) - 4 * k));
+  if (k >= KB / 4) return 0u;
+  uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p + (KB - 4) - 4 * k));
   return __byte_perm(v, 0, 0x0123);
 }
 
-// Byte i (big-endian position, 0 = most significant) of EMSA-PKCS1-v1_5(digest), k = 256.
+// Byte i (big-endian position, 0 = most significant) of EMSA-PKCS1-v1_5(digest), k = KB.
 // Mirrors the layout rsa.VerifyPKCS1v15 checks: 00 01 FF.. 00 prefix digest.
+template <int KB = kRsaBytes>
 __device__ __forceinline__ uint32_t em_byte(int i, const uint8_t* digest, int plen, int dlen, uint32_t hash_alg) {
   const int tlen = plen + dlen;
-  const int t0 = kRsaBytes - tlen;
+  const int t0 = KB - tlen;
   if (i >= t0) {
     int t = i - t0;
     return t < plen ? (uint32_t)c_hash_prefix[hash_alg].bytes[t] : (uint32_t)__ldg(digest + (t - plen));
@@ -87,11 +96,12 @@ __device__ __forceinline__ uint32_t em_byte(int i, const uint8_t* digest, int pl
   if (i == t0 - 1) return 0u;
   return 0xFFu;
 }
+template <int KB = kRsaBytes>
 __device__ __forceinline__ uint32_t em_word(int k, const uint8_t* digest, int plen, int dlen, uint32_t hash_alg) {
-  if (k >= kRsaWords) return 0u;
-  const int b = (kRsaBytes - 4) - 4 * k;
-  return (em_byte(b, digest, plen, dlen, hash_alg) << 24) | (em_byte(b + 1, digest, plen, dlen, hash_alg) << 16) |
-         (em_byte(b + 2, digest, plen, dlen, hash_alg) << 8) | em_byte(b + 3, digest, plen, dlen, hash_alg);
+  if (k >= KB / 4) return 0u;
+  const int b = (KB - 4) - 4 * k;
+  return (em_byte<KB>(b, digest, plen, dlen, hash_alg) << 24) | (em_byte<KB>(b + 1, digest, plen, dlen, hash_alg) << 16) |
+         (em_byte<KB>(b + 2, digest, plen, dlen, hash_alg) << 8) | em_byte<KB>(b + 3, digest, plen, dlen, hash_alg);
 }
 
 // ---- Montgomery product, radix 2^28, T lanes x W digits ---------------------------------------
@@ -168,14 +178,15 @@ __device__ __forceinline__ void canonicalise(uint32_t (&y)[W], const int r) {
 // ---- the kernel -------------------------------------------------------------------------------
 // One group of T lanes per signature; a warp handles 32/T signatures per pass and strides over
 // the batch.  `layout` selects the R^2 table matching T*W digits.
-template <int T, int W, int BLOCK>
+template <int T, int W, int BLOCK, int KB>
 __global__ void __launch_bounds__(BLOCK)
 rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, const uint32_t* __restrict__ key_idx,
                   const uint8_t* __restrict__ sig, const uint8_t* __restrict__ digest, const uint32_t hash_alg,
                   const uint64_t n_items, const uint32_t flags, const uint8_t* __restrict__ pre_status,
                   uint8_t* __restrict__ status) {
-  constexpr int kLayout = (T * W == 74) ? 0 : ((T * W == 76) ? 1 : 2);
-  static_assert(T * W == 74 || T * W == 76 || T * W == 80, "unsupported digit layout");
+  constexpr int kLayout = (T * W == class_digits(KB, 0)) ? 0 : 1;
+  static_assert(T * W == class_digits(KB, 0) || T * W == class_digits(KB, 1), "digit layout does not match the key-size class");
+  static_assert(T * W * kDigitBits >= 8 * KB + 24, "R must exceed 2^24 n");
   constexpr int kGroupsPerWarp = 32 / T;
   const int lane = threadIdx.x & 31;
   const int r = lane & (T - 1);
@@ -193,6 +204,7 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     const bool known = kidx < nkeys;
     if (!known) kidx = 0u;
     const RsaKeyDev* __restrict__ key = keys + kidx;
+    const bool wrong_class = __ldg(&key->kbytes) != (uint32_t)KB;    // len(sig) != k: rsa.VerifyPKCS1v15 fails
 
     uint32_t nd[W], xs[W], xm[W], y[W];
 #pragma unroll
@@ -201,12 +213,12 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     const uint32_t e = __ldg(&key->e);
 
     // s -> radix 2^28 digits (canonical).
-    const uint8_t* sp = sig + item * (uint64_t)kRsaBytes;
+    const uint8_t* sp = sig + item * (uint64_t)KB;
 #pragma unroll
     for (int j = 0; j < W; j++) {
       const int o = kDigitBits * (r * W + j);
       const int wi = o >> 5, sh = o & 31;
-      xs[j] = __funnelshift_r(be_word(sp, wi), be_word(sp, wi + 1), sh) & kDigitMask;
+      xs[j] = __funnelshift_r(be_word<KB>(sp, wi), be_word<KB>(sp, wi + 1), sh) & kDigitMask;
     }
     // s >= n ?  (lexicographic compare across the group, most significant lane wins)
     bool gt = false, lt = false;
@@ -282,8 +294,8 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     for (int j = 0; j < W; j++) {
       const int o = kDigitBits * (r * W + j);
       const int wi = o >> 5, sh = o & 31;
-      const uint32_t lo = em_word(wi, dp, plen, dlen, hash_alg);
-      const uint32_t hi = em_word(wi + 1, dp, plen, dlen, hash_alg);
+      const uint32_t lo = em_word<KB>(wi, dp, plen, dlen, hash_alg);
+      const uint32_t hi = em_word<KB>(wi + 1, dp, plen, dlen, hash_alg);
       const uint32_t emd = __funnelshift_r(lo, hi, sh) & kDigitMask;
       eq = eq && (emd == y[j]);
     }
@@ -291,6 +303,7 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     if (valid && r == 0) {
       uint8_t st = (eqb == gmask) ? (uint8_t)0 : (uint8_t)1;         // BFTQ_ST_OK / BFTQ_ST_BAD_SIGNATURE
       if ((flags & 1u) && s_ge_n) st = 1;                             // BFTQ_F_STRICT_RANGE
+      if (wrong_class) st = 1;
       if (!known) st = 4;                                             // BFTQ_ST_UNKNOWN_SIGNER
       if (pre_status != nullptr) {                                    // decided by the packer (missing, malformed ...)
         const uint8_t pre = __ldg(pre_status + item_raw);

@@ -351,6 +351,7 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
     if (valid && r == 0) {
       uint8_t st = (eqb == gmask) ? (uint8_t)0 : (uint8_t)1;
       if ((flags & 1u) && s_ge_n) st = 1;
+      if (__ldg(&key->nbits) != 2048u) st = 1;             // not this kernel's key class
       if (!known) st = 4;
       if (pre_status != nullptr) {
         const uint8_t pre = __ldg(pre_status + item_raw);

@@ -60,23 +60,27 @@ class Engine:
         return self._lib.bftq_key_count(self._h)
 
     def register_rsa_keys(self, moduli, exps) -> int:
-        """moduli: iterable of Python ints (or (K,256) uint8 big-endian array); returns first index."""
+        """moduli: iterable of Python ints of up to 4096 bits (or a (K,stride) uint8 big-endian array);
+        returns the index of the first new key."""
         if not isinstance(moduli, np.ndarray):
-            moduli = np.frombuffer(b"".join(int(n).to_bytes(256, "big") for n in moduli), dtype=np.uint8)
-        moduli = np.ascontiguousarray(moduli, dtype=np.uint8).reshape(-1, 256)
+            moduli = [int(n) for n in moduli]
+            stride = 256 if all(n.bit_length() <= 2048 for n in moduli) else 512
+            moduli = np.frombuffer(b"".join(n.to_bytes(stride, "big") for n in moduli), dtype=np.uint8).reshape(-1, stride)
+        moduli = np.ascontiguousarray(moduli, dtype=np.uint8)
         exps = np.ascontiguousarray(np.asarray(exps, dtype=np.uint32))
         assert exps.shape[0] == moduli.shape[0]
         first = C.c_uint32()
-        _lib.check(self._lib.bftq_register_rsa_keys(self._h, _ptr(moduli), _ptr(exps), moduli.shape[0], C.byref(first)))
+        _lib.check(self._lib.bftq_register_rsa_keys_k(self._h, _ptr(moduli), moduli.shape[1], _ptr(exps), moduli.shape[0], C.byref(first)))
         return first.value
 
-    def rsa_verify_batch(self, key_idx, sig_be, digest, hash_alg=HASH_SHA256, flags=0, out=None):
-        """Host buffers (numpy or pinned torch tensors).  Returns uint8 status per item."""
+    def rsa_verify_batch(self, key_idx, sig_be, digest, hash_alg=HASH_SHA256, flags=0, out=None, key_bytes=256):
+        """Host buffers (numpy or pinned torch tensors).  Returns uint8 status per item.
+        key_bytes: size class of the batch (128/192/256/384/512); sig_be is (N, key_bytes)."""
         n = int(key_idx.shape[0])
         if out is None:
             out = np.empty(n, dtype=np.uint8)
-        _lib.check(self._lib.bftq_rsa_verify_batch(self._h, _ptr(key_idx), _ptr(sig_be), _ptr(digest),
-                                                   hash_alg, n, flags, _ptr(out)))
+        _lib.check(self._lib.bftq_rsa_verify_batch_k(self._h, key_bytes, _ptr(key_idx), _ptr(sig_be), _ptr(digest),
+                                                     hash_alg, n, flags, _ptr(out)))
         return out
 
     def rsa_verify_batch_dev(self, d_key_idx, d_sig, d_digest, n, d_status, hash_alg=HASH_SHA256, flags=0, stream=0):

@@ -85,10 +85,15 @@ int  bftq_device_sm_count(bftq_engine* e);
  * reached from crypto/pgp/crypto_pgp.go:324,338,490.  Registers `count` RSA public keys:
  * n_be = count x 256 bytes (big-endian modulus, left-padded), e = count public exponents.
  * Precomputes the per-key Montgomery constants once.  Keys are appended; *first_index receives
- * the index of the first new key (indices are what key_idx[] refers to).  Round 1 accepts
- * moduli of 2041..2048 bits (k = 256, what gpg --quick-gen-key rsa2048 produces). */
+ * the index of the first new key (indices are what key_idx[] refers to).  A key's size class is
+ * k = ceil(bits/8) (Go's pub.Size()); classes built: 128, 192, 256, 384, 512 bytes (RSA-1024 ...
+ * RSA-4096).  Exactly-2048-bit moduli (what gpg --quick-gen-key rsa2048 produces) take the
+ * radix-2^32 fast path. */
 int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* exps,
                            uint32_t count, uint32_t* first_index);
+/* Same with moduli of up to 512 bytes: n_be = count x stride bytes, each left-padded. */
+int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t stride, const uint32_t* exps,
+                             uint32_t count, uint32_t* first_index);
 int bftq_key_count(bftq_engine* e);
 
 /* ---- K1: batched RSA PKCS#1 v1.5 verify ------------------------------------------------------
@@ -111,6 +116,16 @@ int bftq_rsa_verify_batch(bftq_engine* e, const uint32_t* key_idx, const uint8_t
 int bftq_rsa_verify_batch_dev(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig_be,
                               const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items,
                               uint32_t flags, uint8_t* d_status, void* cuda_stream);
+
+/* Key-size-class forms: every signature of the batch is key_bytes long (128/192/256/384/512) and
+ * must refer to keys of that class — a key of another class gives BFTQ_ST_BAD_SIGNATURE, as
+ * rsa.VerifyPKCS1v15 rejects len(sig) != k. */
+int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* key_idx, const uint8_t* sig_be,
+                            const uint8_t* digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
+                            uint8_t* out_status);
+int bftq_rsa_verify_batch_dev_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* d_key_idx, const uint8_t* d_sig_be,
+                                const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
+                                uint8_t* d_status, void* cuda_stream);
 
 /* ---- K2: batched wotqs quorum tally ---------------------------------------------------------
  * A quorum descriptor is what wotqs.getQuorumFrom builds (quorum/wotqs/wotqs.go:95-115): a list of
