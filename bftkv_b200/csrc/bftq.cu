@@ -6,6 +6,7 @@
 #include "rsa_verify_r32.cuh"
 #include "tally.cuh"
 #include "lagrange.cuh"
+#include "modexp.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
@@ -634,9 +635,7 @@ int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t
 
 namespace {
 template <int L>
-int lagrange_run(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x, const uint8_t* y_be,
-                 uint64_t n_items, uint8_t* out_be, uint8_t* out_status) {
-  bftq::LagrangeMod<L> M;
+void make_lagrange_mod(const uint8_t* m_be, uint32_t mlen, bftq::LagrangeMod<L>& M) {
   memset(&M, 0, sizeof(M));
   for (uint32_t i = 0; i < mlen; i++) {
     const uint32_t bi = mlen - 1 - i;          // little-endian byte number
@@ -646,7 +645,7 @@ int lagrange_run(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k,
   uint32_t inv = M.m[0];
   for (int i = 0; i < 5; i++) inv *= 2u - M.m[0] * inv;
   M.m0inv = 0u - inv;
-  // R mod m by shift-and-subtract from 1
+  // R mod m and R^2 mod m by shift-and-subtract from 1
   std::vector<uint32_t> r(L + 1, 0u);
   r[0] = 1;
   auto ge_m = [&](const std::vector<uint32_t>& v) {
@@ -660,31 +659,102 @@ int lagrange_run(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k,
     v[L] -= (uint32_t)br;
   };
   while (ge_m(r)) sub_m(r);
-  for (int b = 0; b < 32 * L; b++) {
-    for (int i = L; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
-    r[0] <<= 1;
-    if (ge_m(r)) sub_m(r);
+  for (int pass = 0; pass < 2; pass++) {
+    for (int b = 0; b < 32 * L; b++) {
+      for (int i = L; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+      r[0] <<= 1;
+      if (ge_m(r)) sub_m(r);
+    }
+    for (int i = 0; i < L; i++) (pass == 0 ? M.r1 : M.r2)[i] = r[i];
   }
-  for (int i = 0; i < L; i++) M.r1[i] = r[i];
-  for (int b = 0; b < 32 * L; b++) {
-    for (int i = L; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
-    r[0] <<= 1;
-    if (ge_m(r)) sub_m(r);
-  }
-  for (int i = 0; i < L; i++) M.r2[i] = r[i];
-  Arena a(e);
-  int32_t* d_x; uint8_t *d_y, *d_out, *d_st;
-  a.in(&d_x, x, (size_t)n_items * k);
-  a.in(&d_y, y_be, (size_t)n_items * k * mlen);
-  a.out(&d_out, out_be, (size_t)n_items * mlen);
-  a.out(&d_st, out_status, (size_t)n_items);
-  int rc = a.upload();
-  if (rc) return rc;
+}
+
+int check_modulus(const uint8_t* m_be, uint32_t mlen) {
+  if (mlen == 0 || mlen > 256) return fail(BFTQ_ERR_INVALID_ARG, "modulus length must be 1..256 bytes");
+  if (!(m_be[mlen - 1] & 1)) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be odd");
+  bool gt1 = false;
+  for (uint32_t i = 0; i + 1 < mlen; i++) gt1 = gt1 || m_be[i];
+  if (!gt1 && m_be[mlen - 1] <= 1) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be > 1");
+  return BFTQ_OK;
+}
+
+// lambda / combine launcher on an existing arena stream (device pointers).
+template <int L>
+int launch_lagrange(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* d_x, const uint8_t* d_y, uint64_t n_items,
+                    uint8_t* d_out, uint8_t* d_st, uint8_t* d_lambda, cudaStream_t st) {
+  bftq::LagrangeMod<L> M;
+  make_lagrange_mod<L>(m_be, mlen, M);
   const int block = 128;
-  bftq::lagrange_combine_kernel<L><<<(unsigned)((n_items + block - 1) / block), block, 0, a.stream()>>>(M, k, d_x, d_y, n_items, d_out, d_st);
+  bftq::lagrange_combine_kernel<L><<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(M, k, d_x, d_y, n_items, d_out, d_st, d_lambda);
   CU(cudaGetLastError());
   { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
-  return a.download();
+  return BFTQ_OK;
+}
+int launch_lagrange_any(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* d_x, const uint8_t* d_y,
+                        uint64_t n_items, uint8_t* d_out, uint8_t* d_st, uint8_t* d_lambda, cudaStream_t st) {
+  if (mlen <= 32) return launch_lagrange<8>(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, d_lambda, st);
+  if (mlen <= 64) return launch_lagrange<16>(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, d_lambda, st);
+  if (mlen <= 128) return launch_lagrange<32>(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, d_lambda, st);
+  return launch_lagrange<64>(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, d_lambda, st);
+}
+
+// ---- K5 plumbing ---------------------------------------------------------------------------------
+template <int W>
+int make_moddev(const uint8_t* p_be, uint32_t plen, bftq::ModDev<W>& M) {
+  if (plen != 16u * W) return fail(BFTQ_ERR_INVALID_ARG, "internal: modulus class mismatch");
+  UBig n;
+  from_be(n, p_be, plen);
+  if (bitlen(n) != 128 * W || !(n.w[0] & 1)) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "exponentiation modulus must be odd with exactly 8*len bits");
+  memset(&M, 0, sizeof(M));
+  for (int i = 0; i < 2 * W; i++) { M.n[2 * i] = (uint32_t)n.w[i]; M.n[2 * i + 1] = (uint32_t)(n.w[i] >> 32); }
+  uint32_t n0 = (uint32_t)n.w[0], inv = n0;
+  for (int i = 0; i < 5; i++) inv *= 2u - n0 * inv;
+  M.n0inv = 0u - inv;
+  M.nbytes = plen;
+  UBig y;
+  memset(&y, 0, sizeof(y));
+  y.w[0] = 1;
+  for (int ex = 0; ex < 2 * 128 * W; ex++) dbl_mod(y, n);
+  for (int i = 0; i < 2 * W; i++) { M.r2[2 * i] = (uint32_t)y.w[i]; M.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
+  return BFTQ_OK;
+}
+template <int W>
+int launch_modexp(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_base, const uint8_t* d_exp, uint32_t elen, uint64_t n,
+                  uint8_t* d_out, cudaStream_t st) {
+  bftq::ModDev<W> M;
+  int rc = make_moddev<W>(p_be, plen, M);
+  if (rc) return rc;
+  const uint64_t per_block = 4 * 8;
+  uint64_t grid = std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t)e->sm_count * 4);
+  if (grid < 1) grid = 1;
+  bftq::modexp_kernel<W, 128><<<(unsigned)grid, 128, 0, st>>>(M, d_base, d_exp, elen, n, d_out);
+  CU(cudaGetLastError());
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  return BFTQ_OK;
+}
+template <int W>
+int launch_modprod(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_vals, uint32_t k, uint64_t n, uint8_t* d_out, cudaStream_t st) {
+  bftq::ModDev<W> M;
+  int rc = make_moddev<W>(p_be, plen, M);
+  if (rc) return rc;
+  const uint64_t per_block = 4 * 8;
+  uint64_t grid = std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t)e->sm_count * 4);
+  if (grid < 1) grid = 1;
+  bftq::modprod_kernel<W, 128><<<(unsigned)grid, 128, 0, st>>>(M, d_vals, k, n, d_out);
+  CU(cudaGetLastError());
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  return BFTQ_OK;
+}
+int modexp_any(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_base, const uint8_t* d_exp, uint32_t elen, uint64_t n,
+               uint8_t* d_out, cudaStream_t st) {
+  if (plen == 128) return launch_modexp<8>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st);
+  if (plen == 256) return launch_modexp<16>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st);
+  return fail(BFTQ_ERR_UNSUPPORTED_KEY, "exponentiation modulus must be 128 or 256 bytes (1024 / 2048 bit)");
+}
+int modprod_any(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_vals, uint32_t k, uint64_t n, uint8_t* d_out, cudaStream_t st) {
+  if (plen == 128) return launch_modprod<8>(e, p_be, plen, d_vals, k, n, d_out, st);
+  if (plen == 256) return launch_modprod<16>(e, p_be, plen, d_vals, k, n, d_out, st);
+  return fail(BFTQ_ERR_UNSUPPORTED_KEY, "exponentiation modulus must be 128 or 256 bytes (1024 / 2048 bit)");
 }
 }  // namespace
 
@@ -693,16 +763,128 @@ extern "C" {
 int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x,
                                 const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status) {
   if (!e || !m_be || !x || !y_be || !out_be || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  if (mlen == 0 || mlen > 256 || k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "modulus length must be 1..256 bytes, k 1..255");
-  if (!(m_be[mlen - 1] & 1)) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be odd");
-  bool gt1 = false;
-  for (uint32_t i = 0; i + 1 < mlen; i++) gt1 = gt1 || m_be[i];
-  if (!gt1 && m_be[mlen - 1] <= 1) return fail(BFTQ_ERR_INVALID_ARG, "modulus must be > 1");
+  if (k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "k must be 1..255");
+  int rc = check_modulus(m_be, mlen);
+  if (rc) return rc;
   if (n_items == 0) return BFTQ_OK;
-  if (mlen <= 32) return lagrange_run<8>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
-  if (mlen <= 64) return lagrange_run<16>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
-  if (mlen <= 128) return lagrange_run<32>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
-  return lagrange_run<64>(e, m_be, mlen, k, x, y_be, n_items, out_be, out_status);
+  Arena a(e);
+  int32_t* d_x; uint8_t *d_y, *d_out, *d_st;
+  a.in(&d_x, x, (size_t)n_items * k);
+  a.in(&d_y, y_be, (size_t)n_items * k * mlen);
+  a.out(&d_out, out_be, (size_t)n_items * mlen);
+  a.out(&d_st, out_status, (size_t)n_items);
+  rc = a.upload();
+  if (rc) return rc;
+  rc = launch_lagrange_any(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, nullptr, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
+// ---- K5 ---------------------------------------------------------------------------------------
+int bftq_modexp_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, const uint8_t* base_be, const uint8_t* exp_be, uint32_t elen,
+                      uint64_t n_items, uint8_t* out_be) {
+  if (!e || !m_be || !base_be || !exp_be || !out_be || elen == 0) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  uint8_t *d_b, *d_e, *d_o;
+  a.in(&d_b, base_be, (size_t)n_items * mlen);
+  a.in(&d_e, exp_be, (size_t)n_items * elen);
+  a.out(&d_o, out_be, (size_t)n_items * mlen);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = modexp_any(e, m_be, mlen, d_b, d_e, elen, n_items, d_o, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
+// prod_i Y_i^lambda_i mod p with lambda_i = Lagrange(x_i, xs, q): K3 (lambda) -> K5 modexp -> K5 product.
+static int lagrange_exp_product_dev(bftq_engine* e, Arena& a, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, uint32_t k,
+                                    const int32_t* d_x, const uint8_t* d_y, uint64_t n_items, uint8_t* d_lambda, uint8_t* d_pow, uint8_t* d_dummy_out,
+                                    uint8_t* d_st, uint8_t* d_prod) {
+  // lambda only: feed the combine kernel zero shares (d_pow is zero-initialised scratch of sufficient size is not
+  // needed: y is read but its product is discarded) — reuse d_y's first bytes as y is only multiplied in.
+  int rc = launch_lagrange_any(e, q_be, qlen, k, d_x, d_lambda /* any readable k*qlen bytes per item */, n_items, d_dummy_out, d_st, d_lambda, a.stream());
+  if (rc) return rc;
+  rc = modexp_any(e, p_be, plen, d_y, d_lambda, qlen, n_items * k, d_pow, a.stream());
+  if (rc) return rc;
+  return modprod_any(e, p_be, plen, d_pow, k, n_items, d_prod, a.stream());
+}
+
+int bftq_lagrange_exp_product_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, uint32_t k,
+                                    const int32_t* x, const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status) {
+  if (!e || !p_be || !q_be || !x || !y_be || !out_be || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "k must be 1..255");
+  int rc = check_modulus(q_be, qlen);
+  if (rc) return rc;
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  int32_t* d_x; uint8_t *d_y, *d_lam, *d_pow, *d_tmp, *d_st, *d_out;
+  a.in(&d_x, x, (size_t)n_items * k);
+  a.in(&d_y, y_be, (size_t)n_items * k * plen);
+  a.out(&d_lam, (uint8_t*)nullptr, (size_t)n_items * k * qlen, 0);
+  a.out(&d_pow, (uint8_t*)nullptr, (size_t)n_items * k * plen, 0);
+  a.out(&d_tmp, (uint8_t*)nullptr, (size_t)n_items * qlen, 0);
+  a.out(&d_st, out_status, (size_t)n_items);
+  a.out(&d_out, out_be, (size_t)n_items * plen);
+  rc = a.upload();
+  if (rc) return rc;
+  CU(cudaMemsetAsync(d_lam, 0, (size_t)n_items * k * qlen, a.stream()));
+  rc = lagrange_exp_product_dev(e, a, p_be, plen, q_be, qlen, k, d_x, d_y, n_items, d_lam, d_pow, d_tmp, d_st, d_out);
+  if (rc) return rc;
+  return a.download();
+}
+
+int bftq_dsa_calculate_r_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, uint32_t k,
+                               const int32_t* x, const uint8_t* ri_be, const uint8_t* vi_be, uint64_t n_items, uint8_t* out_r_be,
+                               uint8_t* out_status) {
+  if (!e || !p_be || !q_be || !x || !ri_be || !vi_be || !out_r_be || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "k must be 1..255");
+  if (qlen > 32) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "subgroup order longer than 256 bits");
+  int rc = check_modulus(q_be, qlen);
+  if (rc) return rc;
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  int32_t* d_x; uint8_t *d_ri, *d_vi, *d_lam, *d_pow, *d_tmp, *d_st, *d_st2, *d_prod, *d_v, *d_vinv, *d_rp, *d_out;
+  a.in(&d_x, x, (size_t)n_items * k);
+  a.in(&d_ri, ri_be, (size_t)n_items * k * plen);
+  a.in(&d_vi, vi_be, (size_t)n_items * k * qlen);
+  a.out(&d_lam, (uint8_t*)nullptr, (size_t)n_items * k * qlen, 0);
+  a.out(&d_pow, (uint8_t*)nullptr, (size_t)n_items * k * plen, 0);
+  a.out(&d_tmp, (uint8_t*)nullptr, (size_t)n_items * qlen, 0);
+  a.out(&d_prod, (uint8_t*)nullptr, (size_t)n_items * plen, 0);
+  a.out(&d_v, (uint8_t*)nullptr, (size_t)n_items * qlen, 0);
+  a.out(&d_vinv, (uint8_t*)nullptr, (size_t)n_items * qlen, 0);
+  a.out(&d_rp, (uint8_t*)nullptr, (size_t)n_items * plen, 0);
+  a.out(&d_st2, (uint8_t*)nullptr, (size_t)n_items, 0);
+  a.out(&d_st, out_status, (size_t)n_items);
+  a.out(&d_out, out_r_be, (size_t)n_items * qlen);
+  rc = a.upload();
+  if (rc) return rc;
+  cudaStream_t st = a.stream();
+  CU(cudaMemsetAsync(d_lam, 0, (size_t)n_items * k * qlen, st));
+  // r' = prod R_i^lambda_i mod p                                    (dsa.go:41-46)
+  rc = lagrange_exp_product_dev(e, a, p_be, plen, q_be, qlen, k, d_x, d_ri, n_items, d_lam, d_pow, d_tmp, d_st, d_prod);
+  if (rc) return rc;
+  // v = sum v_i lambda_i mod q                                      (dsa.go:47-48)
+  rc = launch_lagrange_any(e, q_be, qlen, k, d_x, d_vi, n_items, d_v, d_st2, nullptr, st);
+  if (rc) return rc;
+  // v^-1 mod q (q prime: Fermat)                                    (dsa.go:50)
+  {
+    bftq::LagrangeMod<8> M;
+    make_lagrange_mod<8>(q_be, qlen, M);
+    const int block = 128;
+    bftq::fermat_inverse_kernel<8><<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(M, d_v, n_items, d_vinv, d_st);
+    CU(cudaGetLastError());
+    // r = r'^(v^-1) mod p                                           (dsa.go:51)
+    rc = modexp_any(e, p_be, plen, d_prod, d_vinv, qlen, n_items, d_rp, st);
+    if (rc) return rc;
+    // r mod q                                                       (dsa.go:52)
+    bftq::mod_small_kernel<8><<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(M, d_rp, plen, n_items, d_out);
+    CU(cudaGetLastError());
+    std::lock_guard<std::mutex> g(e->mu);
+    e->stats.launches += 2;
+  }
+  return a.download();
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------

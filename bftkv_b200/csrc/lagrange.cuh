@@ -157,7 +157,7 @@ template <int L>
 __global__ void __launch_bounds__(128)
 lagrange_combine_kernel(const LagrangeMod<L> M, const uint32_t k, const int32_t* __restrict__ xs,
                         const uint8_t* __restrict__ ys_be, const uint64_t n_items, uint8_t* __restrict__ out_be,
-                        uint8_t* __restrict__ out_status) {
+                        uint8_t* __restrict__ out_status, uint8_t* __restrict__ out_lambda) {
   const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= n_items) return;
   const int32_t* x = xs + item * k;
@@ -194,6 +194,18 @@ lagrange_combine_kernel(const LagrangeMod<L> M, const uint32_t k, const int32_t*
       small_to_big<L>(tmp, xj, M);
       mont_mul_big<L>(tmp, tmp, M.r2, M);
       mont_mul_big<L>(lam, lam, tmp, M);
+    }
+    if (out_lambda != nullptr) {                                 // lambda_i itself (plain), k x mlen bytes per item
+      uint32_t one[L], lp[L];
+#pragma unroll
+      for (int l = 0; l < L; l++) one[l] = 0;
+      one[0] = 1;
+      mont_mul_big<L>(lp, lam, one, M);
+      uint8_t* lb = out_lambda + (item * k + i) * (uint64_t)M.mlen;
+      for (uint32_t p = 0; p < M.mlen; p++) {
+        const uint32_t bi = M.mlen - 1 - p;
+        lb[p] = okay ? (uint8_t)(lp[bi >> 2] >> (8 * (bi & 3))) : (uint8_t)0;
+      }
     }
     // y_i (big-endian, mlen bytes) -> limbs
     uint32_t y[L];

@@ -28,8 +28,8 @@
 namespace bftq {
 namespace r32 {
 
-constexpr int T = 4;      // lanes per signature
-constexpr int W = 16;     // 32-bit limbs per lane
+constexpr int T = 4;      // lanes per number
+// W = 32-bit limbs per lane: 16 for 2048-bit numbers (the RSA kernel), 8 for 1024-bit ones (modexp).
 
 // ---- carry-chain building blocks ----------------------------------------------------------------
 // One asm statement per chain (8 mad.lo.cc/madc.hi.cc pairs + the carry limb), so ptxas sees the
@@ -50,40 +50,70 @@ constexpr int W = 16;     // 32-bit limbs per lane
     "+r"(p[10]), "+r"(p[11]), "+r"(p[12]), "+r"(p[13]), "+r"(p[14]), "+r"(p[15]), "+r"(c0), "+r"(c1)                      \
   : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(x[8]), "r"(x[10]), "r"(x[12]), "r"(x[14]), "r"(m)
 
-// E/O accumulators of one lane: positions 0..18 (+1 scratch so every chain has two carry limbs).
+#define BFTQ_CHAIN4_BODY(first)                                                              \
+  first " %0, %10, %14, %0;  madc.hi.cc.u32 %1, %10, %14, %1;"                                \
+  "madc.lo.cc.u32 %2, %11, %14, %2;  madc.hi.cc.u32 %3, %11, %14, %3;"                        \
+  "madc.lo.cc.u32 %4, %12, %14, %4;  madc.hi.cc.u32 %5, %12, %14, %5;"                        \
+  "madc.lo.cc.u32 %6, %13, %14, %6;  madc.hi.cc.u32 %7, %13, %14, %7;"                        \
+  "addc.cc.u32 %8, %8, 0; addc.u32 %9, %9, 0;"
+#define BFTQ_CHAIN4_OPS(p, c0, c1, x)                                                                                     \
+  : "+r"(p[0]), "+r"(p[1]), "+r"(p[2]), "+r"(p[3]), "+r"(p[4]), "+r"(p[5]), "+r"(p[6]), "+r"(p[7]), "+r"(c0), "+r"(c1)      \
+  : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(m)
+
+// E/O accumulators of one lane: positions 0..W+2 (+1 scratch so every chain has two carry limbs).
+template <int W>
 struct Acc {
-  uint32_t E[20];
-  uint32_t O[18];
+  uint32_t E[W + 4];
+  uint32_t O[W + 2];
+};
+
+// One carry chain over W/2 (lo,hi) pairs starting at p[0], operand limbs x[0], x[2], ..., carry limbs c0, c1.
+template <int W> struct Chain;
+template <> struct Chain<16> {
+  static __device__ __forceinline__ void run(uint32_t* p, uint32_t& c0, uint32_t& c1, const uint32_t* x, const uint32_t m) {
+    asm volatile(BFTQ_CHAIN8_BODY("mad.lo.cc.u32") BFTQ_CHAIN8_OPS(p, c0, c1, x));
+  }
+  static __device__ __forceinline__ void run_cin(uint32_t* p, uint32_t& c0, uint32_t& c1, const uint32_t* x, const uint32_t m, const uint32_t cin) {
+    asm volatile("{ .reg .u32 t; add.cc.u32 t, %27, 0xffffffff;" BFTQ_CHAIN8_BODY("madc.lo.cc.u32") "}"
+                 BFTQ_CHAIN8_OPS(p, c0, c1, x), "r"(cin));
+  }
+};
+template <> struct Chain<8> {
+  static __device__ __forceinline__ void run(uint32_t* p, uint32_t& c0, uint32_t& c1, const uint32_t* x, const uint32_t m) {
+    asm volatile(BFTQ_CHAIN4_BODY("mad.lo.cc.u32") BFTQ_CHAIN4_OPS(p, c0, c1, x));
+  }
+  static __device__ __forceinline__ void run_cin(uint32_t* p, uint32_t& c0, uint32_t& c1, const uint32_t* x, const uint32_t m, const uint32_t cin) {
+    asm volatile("{ .reg .u32 t; add.cc.u32 t, %15, 0xffffffff;" BFTQ_CHAIN4_BODY("madc.lo.cc.u32") "}"
+                 BFTQ_CHAIN4_OPS(p, c0, c1, x), "r"(cin));
+  }
 };
 
 // offset 0: even limbs -> E pairs (k,k+1), odd limbs -> O pairs (O[k-1],O[k]).  `cin` (0/1) enters
 // the even chain at position 0.
-__device__ __forceinline__ void mac_off0_even(Acc& A, const uint32_t (&x)[W], const uint32_t m, const uint32_t cin) {
-  uint32_t* p = A.E;
-  asm volatile("{ .reg .u32 t; add.cc.u32 t, %27, 0xffffffff;" BFTQ_CHAIN8_BODY("madc.lo.cc.u32") "}"
-               BFTQ_CHAIN8_OPS(p, A.E[16], A.E[17], x), "r"(cin));
+template <int W>
+__device__ __forceinline__ void mac_off0_even(Acc<W>& A, const uint32_t (&x)[W], const uint32_t m, const uint32_t cin) {
+  Chain<W>::run_cin(A.E, A.E[W], A.E[W + 1], x, m, cin);
 }
-__device__ __forceinline__ void mac_off0_even_nocin(Acc& A, const uint32_t (&x)[W], const uint32_t m) {
-  uint32_t* p = A.E;
-  asm volatile(BFTQ_CHAIN8_BODY("mad.lo.cc.u32") BFTQ_CHAIN8_OPS(p, A.E[16], A.E[17], x));
+template <int W>
+__device__ __forceinline__ void mac_off0_even_nocin(Acc<W>& A, const uint32_t (&x)[W], const uint32_t m) {
+  Chain<W>::run(A.E, A.E[W], A.E[W + 1], x, m);
 }
-__device__ __forceinline__ void mac_off0_odd(Acc& A, const uint32_t (&x)[W], const uint32_t m) {
-  uint32_t* p = A.O;
-  const uint32_t* xo = x + 1;              // x[1], x[3], ...
-  asm volatile(BFTQ_CHAIN8_BODY("mad.lo.cc.u32") BFTQ_CHAIN8_OPS(p, A.O[16], A.O[17], xo));
+template <int W>
+__device__ __forceinline__ void mac_off0_odd(Acc<W>& A, const uint32_t (&x)[W], const uint32_t m) {
+  Chain<W>::run(A.O, A.O[W], A.O[W + 1], x + 1, m);          // x[1], x[3], ...
 }
 // offset 1: even limbs -> O pairs (O[k],O[k+1]), odd limbs -> E pairs (E[k+1],E[k+2]).
-__device__ __forceinline__ void mac_off1_even(Acc& A, const uint32_t (&x)[W], const uint32_t m) {
-  uint32_t* p = A.O;
-  asm volatile(BFTQ_CHAIN8_BODY("mad.lo.cc.u32") BFTQ_CHAIN8_OPS(p, A.O[16], A.O[17], x));
+template <int W>
+__device__ __forceinline__ void mac_off1_even(Acc<W>& A, const uint32_t (&x)[W], const uint32_t m) {
+  Chain<W>::run(A.O, A.O[W], A.O[W + 1], x, m);
 }
-__device__ __forceinline__ void mac_off1_odd(Acc& A, const uint32_t (&x)[W], const uint32_t m) {
-  uint32_t* p = A.E + 2;
-  const uint32_t* xo = x + 1;
-  asm volatile(BFTQ_CHAIN8_BODY("mad.lo.cc.u32") BFTQ_CHAIN8_OPS(p, A.E[18], A.E[19], xo));
+template <int W>
+__device__ __forceinline__ void mac_off1_odd(Acc<W>& A, const uint32_t (&x)[W], const uint32_t m) {
+  Chain<W>::run(A.E + 2, A.E[W + 2], A.E[W + 3], x + 1, m);
 }
 
 // Ripple-add a 32-bit value into v[0..15]; returns the carry out (0/1).
+template <int W>
 __device__ __forceinline__ uint32_t ripple_add(uint32_t (&v)[W], const uint32_t x) {
   uint32_t c;
   asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(v[0]) : "r"(x));
@@ -93,6 +123,7 @@ __device__ __forceinline__ uint32_t ripple_add(uint32_t (&v)[W], const uint32_t 
   return c;
 }
 // v -= x (one limb), returns borrow out (0/1).
+template <int W>
 __device__ __forceinline__ uint32_t ripple_sub(uint32_t (&v)[W], const uint32_t x) {
   uint32_t b;
   asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(v[0]) : "r"(x));
@@ -102,6 +133,7 @@ __device__ __forceinline__ uint32_t ripple_sub(uint32_t (&v)[W], const uint32_t 
   return b & 1u;
 }
 // d = v - n (limb-wise with borrow chain), returns borrow out (0/1).
+template <int W>
 __device__ __forceinline__ uint32_t sub_n(uint32_t (&d)[W], const uint32_t (&v)[W], const uint32_t (&n)[W]) {
   uint32_t b;
   asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d[0]) : "r"(v[0]), "r"(n[0]));
@@ -122,15 +154,16 @@ __device__ __forceinline__ uint32_t lane_carry_in(const uint32_t gbits, const ui
   return r == 0 ? 0u : (r == 1 ? c1 : (r == 2 ? c2 : c3));
 }
 
-// out = a * b * 2^-2048 mod n, out < 2^2048 ("almost Montgomery").  a, b < 2^2048 as 16 limbs/lane.
+// out = a * b * R^-1 mod n with R = 2^(128 W), out < R ("almost Montgomery").  a, b < R as W limbs/lane.
 // All 32 lanes of the warp must call this together.
+template <int W>
 __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)[W], const uint32_t (&b)[W],
                                          const uint32_t (&n)[W], const uint32_t n0inv, const int r, const int gbase) {
-  Acc A;
+  Acc<W> A;
 #pragma unroll
-  for (int k = 0; k < 20; k++) A.E[k] = 0u;
+  for (int k = 0; k < W + 4; k++) A.E[k] = 0u;
 #pragma unroll
-  for (int k = 0; k < 18; k++) A.O[k] = 0u;
+  for (int k = 0; k < W + 2; k++) A.O[k] = 0u;
   uint32_t cin = 0u;      // 1-bit carry pending at position 0
   uint32_t Z = 0u;        // odd-side limb pending at position 0 (the upper half of the O pair the shift cut)
 #pragma unroll 1
@@ -167,13 +200,13 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
       if (r == T - 1) { r0 = 0u; r1 = 0u; }
       // shift down two limbs (register renaming)
 #pragma unroll
-      for (int k = 0; k < 18; k++) A.E[k] = A.E[k + 2];
-      A.E[18] = 0u; A.E[19] = 0u;
+      for (int k = 0; k < W + 2; k++) A.E[k] = A.E[k + 2];
+      A.E[W + 2] = 0u; A.E[W + 3] = 0u;
 #pragma unroll
-      for (int k = 0; k < 16; k++) A.O[k] = A.O[k + 2];
-      A.O[16] = 0u; A.O[17] = 0u;
+      for (int k = 0; k < W; k++) A.O[k] = A.O[k + 2];
+      A.O[W] = 0u; A.O[W + 1] = 0u;
       asm volatile("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, 0; addc.u32 %3, %3, 0;"
-                   : "+r"(A.E[14]), "+r"(A.E[15]), "+r"(A.E[16]), "+r"(A.E[17]) : "r"(r0), "r"(r1));
+                   : "+r"(A.E[W - 2]), "+r"(A.E[W - 1]), "+r"(A.E[W]), "+r"(A.E[W + 1]) : "r"(r0), "r"(r1));
     }
   }
   // ---- merge E, O and the pending carry into 16 limbs + overflow ------------------------------
@@ -181,7 +214,7 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
   asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(v[0]) : "r"(A.E[0]), "r"(Z));
 #pragma unroll
   for (int k = 1; k < W; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(v[k]) : "r"(A.E[k]), "r"(A.O[k - 1]));
-  asm volatile("addc.u32 %0, %1, %2;" : "=r"(hi) : "r"(A.E[16]), "r"(A.O[15]));
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(hi) : "r"(A.E[W]), "r"(A.O[W - 1]));
   // the lane's overflow (a few units) belongs to the lane above; the top lane's is bit 2048+
   uint32_t from_below = __shfl_up_sync(kFull, hi, 1, T);
   if (r == 0) from_below = 0u;
@@ -218,6 +251,7 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
 }
 
 // x >= n ?  (lane-distributed compare)
+template <int W>
 __device__ __forceinline__ bool group_ge(const uint32_t (&x)[W], const uint32_t (&n)[W], const int gbase) {
   bool gt = false, lt = false;
 #pragma unroll
@@ -231,6 +265,7 @@ __device__ __forceinline__ bool group_ge(const uint32_t (&x)[W], const uint32_t 
 }
 
 // x -= n when x >= n (x < 2n on entry).
+template <int W>
 __device__ __forceinline__ void cond_sub(uint32_t (&x)[W], const uint32_t (&n)[W], const int r, const int gbase) {
   const bool ge = group_ge(x, n, gbase);
   uint32_t d[W];
@@ -264,6 +299,7 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
                       const uint8_t* __restrict__ sig, const uint8_t* __restrict__ digest, const uint32_t hash_alg,
                       const uint64_t n_items, const uint32_t flags, const uint8_t* __restrict__ pre_status,
                       uint8_t* __restrict__ status) {
+  constexpr int W = 16;
   constexpr int kGroupsPerWarp = 32 / T;
   // s*R mod n is only needed again for exponents with interior 1 bits (never for 65537): park it in
   // shared memory instead of 16 registers.

@@ -148,6 +148,46 @@ class Engine:
         _lib.check(self._lib.bftq_lagrange_combine_batch(self._h, _ptr(mb), mlen, k, _ptr(x), _ptr(y_be), B, _ptr(out), _ptr(st)))
         return out, st
 
+    # ---- K5 ----
+    @staticmethod
+    def _be(vals, width):
+        return np.frombuffer(b"".join(int(v).to_bytes(width, "big") for v in vals), np.uint8).copy()
+
+    def modexp_batch(self, m: int, bases, exps, elen=None):
+        """[pow(b, e, m)] for a shared odd modulus of exactly 1024 or 2048 bits."""
+        mlen = (m.bit_length() + 7) // 8
+        elen = elen or max(1, max((int(e).bit_length() + 7) // 8 for e in exps))
+        n = len(bases)
+        out = np.empty((n, mlen), np.uint8)
+        mb, bb, eb = self._be([m], mlen), self._be(bases, mlen), self._be(exps, elen)      # keep the buffers alive across the call
+        _lib.check(self._lib.bftq_modexp_batch(self._h, _ptr(mb), mlen, _ptr(bb), _ptr(eb), elen, n, _ptr(out)))
+        return [int.from_bytes(bytes(o), "big") for o in out]
+
+    def lagrange_exp_product_batch(self, p: int, q: int, x, ys):
+        """auth.calculateSharedSecret: prod_j ys[i][j]^lambda_j mod p.  x: (B,k) ints, ys: B lists of k ints."""
+        plen, qlen = (p.bit_length() + 7) // 8, (q.bit_length() + 7) // 8
+        x = np.ascontiguousarray(x, np.int32)
+        B, k = x.shape
+        yb = self._be([v for row in ys for v in row], plen)
+        out, st = np.empty((B, plen), np.uint8), np.empty(B, np.uint8)
+        pb, qb = self._be([p], plen), self._be([q], qlen)
+        _lib.check(self._lib.bftq_lagrange_exp_product_batch(self._h, _ptr(pb), plen, _ptr(qb), qlen, k,
+                                                             _ptr(x), _ptr(yb), B, _ptr(out), _ptr(st)))
+        return [int.from_bytes(bytes(o), "big") for o in out], st
+
+    def dsa_calculate_r_batch(self, p: int, q: int, x, ris, vis):
+        """dsa.CalculateR per item over k partial results (x_i, R_i, v_i)."""
+        plen, qlen = (p.bit_length() + 7) // 8, (q.bit_length() + 7) // 8
+        x = np.ascontiguousarray(x, np.int32)
+        B, k = x.shape
+        rb = self._be([v for row in ris for v in row], plen)
+        vb = self._be([v for row in vis for v in row], qlen)
+        out, st = np.empty((B, qlen), np.uint8), np.empty(B, np.uint8)
+        pb, qb = self._be([p], plen), self._be([q], qlen)
+        _lib.check(self._lib.bftq_dsa_calculate_r_batch(self._h, _ptr(pb), plen, _ptr(qb), qlen, k,
+                                                        _ptr(x), _ptr(rb), _ptr(vb), B, _ptr(out), _ptr(st)))
+        return [int.from_bytes(bytes(o), "big") for o in out], st
+
     # ---- K4 ----
     def pgp_digest_batch(self, datas, suffixes, data_idx=None, hash_alg=HASH_SHA256):
         """datas: list of bytes (TBS strings); suffixes: list of bytes (one per signature)."""

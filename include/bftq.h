@@ -194,6 +194,25 @@ int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint
 int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x,
                                 const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status);
 
+/* ---- K5: Lagrange in the exponent -------------------------------------------
+ * out[i] = base[i]^exp[i] mod m: big.Int.Exp with a shared odd modulus of exactly 1024 or 2048 bits
+ * (mlen = 128 / 256); base: n_items x mlen, exp: n_items x elen bytes, all big-endian. */
+int bftq_modexp_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, const uint8_t* base_be, const uint8_t* exp_be,
+                      uint32_t elen, uint64_t n_items, uint8_t* out_be);
+/* AuthClient.calculateSharedSecret (crypto/auth/auth.go:386-399) and the first half of CalculateR:
+ * out[i] = prod_j y[i][j]^lambda_j mod p,  lambda_j = sss.Lagrange(x[i][j], x[i][*], q).
+ * p: plen = 128/256 bytes; q: any odd modulus up to 256 bytes (auth uses q = (p-1)/2). */
+int bftq_lagrange_exp_product_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen,
+                                    uint32_t k, const int32_t* x, const uint8_t* y_be, uint64_t n_items, uint8_t* out_be,
+                                    uint8_t* out_status);
+/* dsaGroupOperations.CalculateR (crypto/threshold/dsa/dsa.go:33-52):
+ * r = (prod R_i^lambda_i mod p)^((sum v_i lambda_i)^-1 mod q) mod p mod q, per item over its k
+ * partial results (x_i, R_i, v_i); q prime, <= 256 bits.  out_r_be: n_items x qlen (left-padded, as
+ * formatDSA lays r out, dsa_core.go:375-387). */
+int bftq_dsa_calculate_r_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, uint32_t k,
+                               const int32_t* x, const uint8_t* ri_be, const uint8_t* vi_be, uint64_t n_items,
+                               uint8_t* out_r_be, uint8_t* out_status);
+
 /* ---- K4: batched OpenPGP v4 signature digest --------------------------------------------------
  * Replaces hashForSignature + the hash-suffix step of packet.PublicKey.VerifySignature
  * (x/crypto, reached from crypto_pgp.go:324,338,490): digest_i = H(data[data_idx[i]] || suffix_i).

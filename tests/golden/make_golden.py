@@ -93,6 +93,14 @@ sss = {"auth_test": {"q": 1237, "poly": [1234, 166, 94, 666], "xs": [2, 4, 5, 6]
                       "shares": [[1, 923], [2, 1085], [3, 768], [4, 257], [5, 1074], [6, 1030]]},
        "sss_test": {"secret": b"secret".hex(), "n": 10, "k": 7}}
 
+dsa = {}
+dt = "/root/reference/crypto/threshold/dsa/dsa_test.go"
+if os.path.exists(dt):                      # P, Q, G constants of dsa_test.go:26-28 (numbers only)
+    import re
+    src = open(dt).read()
+    dsa = {k: re.search(r'%sstr = "([0-9A-F]+)"' % k, src).group(1) for k in "PQG"}
+    dsa["source"] = "crypto/threshold/dsa/dsa_test.go:26-28 (parameters of dsa/test.pkcs8)"
+
 json.dump({"generator": "tests/golden/make_golden.py", "gpg": "2.4.4", "keys": keys, "cases": cases,
-           "ref_rsa_kat": ref, "sss": sss}, open(OUT, "w"), indent=0)
+           "ref_rsa_kat": ref, "sss": sss, "dsa_test": dsa}, open(OUT, "w"), indent=0)
 print("wrote", OUT, len(cases), "cases")
