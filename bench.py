@@ -239,6 +239,69 @@ def run_gpu(args, rank, local_rank, world):
     q_ms = q0.elapsed_time(q1)
     assert np.array_equal(dq_st.cpu().numpy(), ro["expect_status"]), "config-3 statuses differ from expectation"
     accepted = int((dq_win.cpu().numpy().astype(np.uint32) != 0xFFFFFFFF).sum())
+    # ---- secondary: BASELINE configs[3] — 262144 Ed25519 verifies (K = 15 keys) + Lagrange combines ----
+    # (the reference itself cannot verify Ed25519; reported for completeness of the configs)
+    ed = None
+    if rank == 0 and not args.skip_ed25519:
+        from cryptography.hazmat.primitives import serialization
+        from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+        from concurrent.futures import ThreadPoolExecutor
+        import random as _r
+        rg = _r.Random(0xBF7C0005)
+        sks = [Ed25519PrivateKey.from_private_bytes(bytes(rg.randrange(256) for _ in range(32))) for _ in range(15)]
+        pk_arr = np.frombuffer(b"".join(k.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw) for k in sks),
+                               np.uint8).reshape(15, 32).copy()
+        NE = 262144
+        e_idx = np.random.default_rng(5).integers(0, 15, NE).astype(np.uint32)
+        e_msg = np.random.default_rng(6).integers(0, 256, (NE, 32), dtype=np.uint8)
+        e_sig = np.empty((NE, 64), np.uint8)
+
+        def sign_range(lo_hi):
+            for i in range(*lo_hi):
+                e_sig[i] = np.frombuffer(sks[e_idx[i]].sign(e_msg[i].tobytes()), np.uint8)
+        nth = max(1, host_cores())
+        with ThreadPoolExecutor(nth) as ex:
+            list(ex.map(sign_range, [(lo, min(NE, lo + 4096)) for lo in range(0, NE, 4096)]))
+        e_sig[::97, 7] ^= 1                                        # 1 % corrupted
+        de = [torch.from_numpy(x).to(dev) for x in (pk_arr, e_idx.astype(np.int32), e_sig, e_msg)]
+        de_st = torch.empty(NE, dtype=torch.uint8, device=dev)
+        import ctypes as C
+        from bftkv_b200 import _lib as L_
+
+        def estep():
+            L_.check(eng._lib.bftq_ed25519_verify_batch_dev(eng._h, C.c_void_p(de[0].data_ptr()), 15, C.c_void_p(de[1].data_ptr()),
+                                                            C.c_void_p(de[2].data_ptr()), C.c_void_p(de[3].data_ptr()), NE,
+                                                            C.c_void_p(de_st.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        estep()
+        stream.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(3):
+            estep()
+        a1.record(stream)
+        stream.synchronize()
+        e_ms = a0.elapsed_time(a1) / 3
+        bad = int((de_st != 0).sum())
+        assert bad == len(range(0, NE, 97)), "Ed25519 statuses differ from expectation"
+        # Lagrange combine, 2t = 10 of n = 15 shares over the P-256 group order (host API, incl. copies)
+        from oracle import sss_oracle as sss_
+        q256 = 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551
+        Bc, kc = NE // 15, 10
+        rgen = np.random.default_rng(7)
+        xs = np.stack([rgen.permutation(15)[:kc] + 1 for _ in range(Bc)]).astype(np.int32)
+        ysb = rgen.integers(0, 256, (Bc, kc, 32), dtype=np.uint8)
+        ysb[:, :, 0] &= 0x7F
+        eng.lagrange_combine_batch(q256, xs[:64], ysb[:64])
+        t0c = time.perf_counter()
+        outc, stc = eng.lagrange_combine_batch(q256, xs, ysb)
+        c_s = time.perf_counter() - t0c
+        j = 12345 % Bc
+        exp_j = sss_.calculate_secret([(int(xs[j, i]), int.from_bytes(ysb[j, i].tobytes(), "big")) for i in range(kc)], q256)
+        assert int.from_bytes(outc[j].tobytes(), "big") == exp_j and not stc.any()
+        ed = {"metric": "ed25519_verifies_per_sec", "value": NE / (e_ms * 1e-3), "unit": "verifies/s", "ms_per_step": e_ms,
+              "config": {"workload": "262144 Ed25519 verifies over 15 keys, 32-byte messages (BASELINE configs[3]); 1% corrupted",
+                         "note": "no reference behaviour exists: x/crypto/openpgp has no EdDSA; checked against OpenSSL"},
+              "lagrange_combines_per_sec": Bc / c_s, "lagrange_config": "%d combines, 10 of 15 shares, P-256 order, host API incl. copies" % Bc}
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, q_ms], dtype=torch.float64, device=dev)
@@ -286,6 +349,7 @@ def run_gpu(args, rank, local_rank, world):
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "algorithmic_bytes_per_verify": BYTES_PER_VERIFY}},
         "clocks": clocks,
+        "ed25519": ed,
     }
     if world == 1:
         threads = host_cores()
@@ -307,6 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--copies", type=int, default=8)
+    ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -7,6 +7,7 @@
 #include "tally.cuh"
 #include "lagrange.cuh"
 #include "modexp.cuh"
+#include "ed25519.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
@@ -467,6 +468,41 @@ int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* 
   int rc = a.upload();
   if (rc) return rc;
   rc = launch_rsa_any(e, d_idx, d_sig, d_dig, hash_alg, n_items, flags, nullptr, d_st, a.stream(), (int)key_bytes);
+  if (rc) return rc;
+  return a.download();
+}
+
+// ---- K1b --------------------------------------------------------------------------------------
+int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* d_pubkeys, uint32_t n_keys, const uint32_t* d_key_idx,
+                                  const uint8_t* d_sig, const uint8_t* d_msg, uint64_t n_items, uint8_t* d_status,
+                                  void* cuda_stream) {
+  if (!e || !d_pubkeys || !d_key_idx || !d_sig || !d_msg || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_items == 0) return BFTQ_OK;
+  CU(cudaSetDevice(e->device));
+  const int block = 128;
+  bftq::ed25519_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, (cudaStream_t)cuda_stream>>>(
+      d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_status);
+  CU(cudaGetLastError());
+  std::lock_guard<std::mutex> g(e->mu);
+  e->stats.launches += 1;
+  e->stats.items += n_items;
+  return BFTQ_OK;
+}
+
+int bftq_ed25519_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* key_idx,
+                              const uint8_t* sig, const uint8_t* msg, uint64_t n_items, uint8_t* out_status) {
+  if (!e || !pubkeys || !key_idx || !sig || !msg || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  uint8_t *d_pk, *d_sig, *d_msg, *d_st; uint32_t* d_idx;
+  a.in(&d_pk, pubkeys, (size_t)std::max<uint32_t>(n_keys, 1) * 32, (size_t)n_keys * 32);
+  a.in(&d_idx, key_idx, (size_t)n_items);
+  a.in(&d_sig, sig, (size_t)n_items * 64);
+  a.in(&d_msg, msg, (size_t)n_items * 32);
+  a.out(&d_st, out_status, (size_t)n_items);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = bftq_ed25519_verify_batch_dev(e, d_pk, n_keys, d_idx, d_sig, d_msg, n_items, d_st, a.stream());
   if (rc) return rc;
   return a.download();
 }

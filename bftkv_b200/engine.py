@@ -148,6 +148,15 @@ class Engine:
         _lib.check(self._lib.bftq_lagrange_combine_batch(self._h, _ptr(mb), mlen, k, _ptr(x), _ptr(y_be), B, _ptr(out), _ptr(st)))
         return out, st
 
+    # ---- K1b ----
+    def ed25519_verify_batch(self, pubkeys, key_idx, sig, msg):
+        """pubkeys (K,32), key_idx (N,), sig (N,64), msg (N,32) uint8/uint32 arrays -> status (N,)."""
+        pubkeys = np.ascontiguousarray(pubkeys, np.uint8)
+        n = int(key_idx.shape[0])
+        out = np.empty(n, np.uint8)
+        _lib.check(self._lib.bftq_ed25519_verify_batch(self._h, _ptr(pubkeys), pubkeys.shape[0], _ptr(key_idx), _ptr(sig), _ptr(msg), n, _ptr(out)))
+        return out
+
     # ---- K5 ----
     @staticmethod
     def _be(vals, width):

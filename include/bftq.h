@@ -127,6 +127,18 @@ int bftq_rsa_verify_batch_dev_k(bftq_engine* e, uint32_t key_bytes, const uint32
                                 const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
                                 uint8_t* d_status, void* cuda_stream);
 
+/* ---- K1b: batched Ed25519 verify (BASELINE config 4) ------------------------------------------
+ * NOT a replacement of anything in the reference: golang.org/x/crypto/openpgp @53104e6ec876 has no
+ * EdDSA (algorithm 22) and skips such keys.  RFC 8032 pure Ed25519 as GnuPG uses it in OpenPGP: the
+ * signed "message" is the 32-byte v4 signature digest.  pubkeys: n_keys x 32 (compressed A),
+ * sig: n_items x 64 (R || S), msg: n_items x 32.  out_status: BFTQ_ST_OK / _BAD_SIGNATURE /
+ * _UNKNOWN_SIGNER.  Rejects S >= L and non-canonical / off-curve A like Go's crypto/ed25519. */
+int bftq_ed25519_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* key_idx,
+                              const uint8_t* sig, const uint8_t* msg, uint64_t n_items, uint8_t* out_status);
+int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* d_pubkeys, uint32_t n_keys, const uint32_t* d_key_idx,
+                                  const uint8_t* d_sig, const uint8_t* d_msg, uint64_t n_items, uint8_t* d_status,
+                                  void* cuda_stream);
+
 /* ---- K2: batched wotqs quorum tally ---------------------------------------------------------
  * A quorum descriptor is what wotqs.getQuorumFrom builds (quorum/wotqs/wotqs.go:95-115): a list of
  * quorum cliques qc{nodes,f,min,threshold,suff} (wotqs.go:16-22, values from newQC :36-70).

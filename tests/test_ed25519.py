@@ -1,0 +1,137 @@
+"""K1b Ed25519 (BASELINE config 4).  The reference cannot verify Ed25519 at all (x/crypto/openpgp
+has no EdDSA), so parity is pinned on RFC 8032 test vectors, OpenSSL (`cryptography`) and
+libsodium (`pynacl`) instead.  CPU tests run the kernel's own __host__ __device__ arithmetic compiled
+for the host (tests/harness/ed25519_host.cpp); the gpu test runs the kernel through the C ABI."""
+import ctypes
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 2 ** 255 - 19
+L = 2 ** 252 + 27742317777372353535851937790883648493
+
+# RFC 8032 §7.1 test vectors 1-3 (secret key, public key, message, signature)
+RFC8032 = [
+    ("d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a", "",
+     "e5564300c360ac729086e2cc806e828a84877f1eb8e5d974d873e065224901555fb8821590a33bacc61e39701cf9b46bd25bf5f0595bbe24655141438e7a100b"),
+    ("3d4017c3e843895a92b70aa74d1b7ebc9c982ccf2ec4968cc0cd55f12af4660c", "72",
+     "92a009a9f0d4cab8720e820b5f642540a2b27b5416503f8fb3762223ebdb69da085ac1e43e15996e458f3613d0f11d8c387b2eaeb4302aeeb00d291612bb0c00"),
+    ("fc51cd8e6218a1a38da47ed00230f0580816ed13ba3303ac5deb911548908025", "af82",
+     "6291d657deec24024827e69c3abe01a30ce548a284743a445e3680d7db5ac3ac18ff9b538d16f290ae67f760984dc6594a7c15e9716ed28dc027beceea1ec40a"),
+]
+
+
+@pytest.fixture(scope="module")
+def host():
+    so = os.path.join(ROOT, "tests", "harness", "libedhost.so")
+    src = os.path.join(ROOT, "tests", "harness", "ed25519_host.cpp")
+    hdr = os.path.join(ROOT, "bftkv_b200", "csrc", "ed25519.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def make_sigs(n, n_keys, seed):
+    from cryptography.hazmat.primitives import serialization
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    rng = random.Random(seed)
+    sks = [Ed25519PrivateKey.from_private_bytes(bytes(rng.randrange(256) for _ in range(32))) for _ in range(n_keys)]
+    pks = [k.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw) for k in sks]
+    kidx = np.array([rng.randrange(n_keys) for _ in range(n)], np.uint32)
+    msg = np.frombuffer(bytes(rng.randrange(256) for _ in range(32 * n)), np.uint8).reshape(n, 32).copy()
+    sig = np.empty((n, 64), np.uint8)
+    for i in range(n):
+        sig[i] = np.frombuffer(sks[kidx[i]].sign(msg[i].tobytes()), np.uint8)
+    return sks, pks, kidx, msg, sig, rng
+
+
+def openssl_ok(sk, sig, msg):
+    try:
+        sk.public_key().verify(sig, msg)
+        return True
+    except Exception:
+        return False
+
+
+def test_field_and_scalar_arithmetic(host):
+    rng = random.Random(1)
+    out = ctypes.create_string_buffer(32)
+    b = lambda x: int(x).to_bytes(32, "little")
+    for i in range(1500):
+        x, y = rng.randrange(P), rng.randrange(P)
+        if i % 50 == 0:
+            x = P - 1
+        if i % 77 == 0:
+            y = P - 1 - (i % 3)
+        host.ed_fe_mul_host(b(x), b(y), out)
+        assert int.from_bytes(out.raw, "little") == x * y % P
+        host.ed_fe_addsubmul_host(b(x), b(y), out)
+        assert int.from_bytes(out.raw, "little") == (x + y) * (x - y) % P
+    for _ in range(40):
+        x = rng.randrange(1, P)
+        host.ed_fe_invert_host(b(x), out)
+        assert int.from_bytes(out.raw, "little") == pow(x, -1, P)
+    for v in [bytes(64), b"\xff" * 64, L.to_bytes(32, "little") + bytes(32), (L - 1).to_bytes(32, "little") + bytes(32)] + [os.urandom(64) for _ in range(100)]:
+        host.ed_sc_reduce_host(v, out)
+        assert int.from_bytes(out.raw, "little") == int.from_bytes(v, "little") % L
+
+
+def test_rfc8032_vectors_and_openssl(host):
+    import nacl.exceptions
+    import nacl.signing
+    for pk, msg, sig in RFC8032:
+        pk, msg, sig = bytes.fromhex(pk), bytes.fromhex(msg), bytes.fromhex(sig)
+        # the kernel signs/verifies 32-byte digests; the core takes k = H(R||A||M) for any M
+        k = hashlib.sha512(sig[:32] + pk + msg).digest()
+        assert host.ed_verify_core_host(sig, pk, k) == 1
+        bad = bytearray(sig); bad[5] ^= 2
+        assert host.ed_verify_core_host(bytes(bad), pk, hashlib.sha512(bytes(bad[:32]) + pk + msg).digest()) == 0
+    sks, pks, kidx, msg, sig, rng = make_sigs(120, 5, 3)
+    for i in range(120):
+        pk, m = pks[kidx[i]], msg[i].tobytes()
+        s = bytearray(sig[i].tobytes())
+        if i % 2:
+            s[rng.randrange(64)] ^= 1 << rng.randrange(8)
+        s = bytes(s)
+        got = host.ed_verify_core_host(s, pk, hashlib.sha512(s[:32] + pk + m).digest()) == 1
+        assert got == openssl_ok(sks[kidx[i]], s, m)
+        try:
+            nacl.signing.VerifyKey(pk).verify(m, s)
+            sodium = True
+        except nacl.exceptions.BadSignatureError:
+            sodium = False
+        assert got == sodium
+    # non-canonical S (S + L), non-canonical / off-curve A
+    s0 = sig[0].tobytes()
+    S = int.from_bytes(s0[32:], "little") + L
+    pk0, m0 = pks[kidx[0]], msg[0].tobytes()
+    if S < 2 ** 256:
+        s1 = s0[:32] + S.to_bytes(32, "little")
+        assert host.ed_verify_core_host(s1, pk0, hashlib.sha512(s1[:32] + pk0 + m0).digest()) == 0
+    for badpk in [(P + 1).to_bytes(32, "little"), (2).to_bytes(32, "little"), b"\xff" * 32]:
+        assert host.ed_verify_core_host(s0, badpk, hashlib.sha512(s0[:32] + badpk + m0).digest()) == 0
+
+
+@pytest.mark.gpu
+def test_ed25519_gpu_batch(engine):
+    n = 4096
+    sks, pks, kidx, msg, sig, rng = make_sigs(n, 15, 0xBF7C0005)          # config 4: K = 15 keys
+    expect = np.zeros(n, np.uint8)
+    for i in range(n):
+        if rng.random() < 0.3:
+            sig[i, rng.randrange(64)] ^= np.uint8(1 << rng.randrange(8))
+            expect[i] = 0 if openssl_ok(sks[kidx[i]], sig[i].tobytes(), msg[i].tobytes()) else 1
+    unk = [5, 77, 901]
+    kidx[unk] = 99
+    expect[unk] = 4
+    pk_arr = np.frombuffer(b"".join(pks), np.uint8).reshape(15, 32).copy()
+    got = engine.ed25519_verify_batch(pk_arr, kidx, sig, msg)
+    assert np.array_equal(got, expect)
+    assert (got == 0).sum() > 2500 and (got == 1).sum() > 1000
+    for size in (1, 2, 31, 129):
+        assert np.array_equal(engine.ed25519_verify_batch(pk_arr, kidx[:size].copy(), sig[:size].copy(), msg[:size].copy()), expect[:size])
