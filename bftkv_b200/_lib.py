@@ -67,6 +67,10 @@ def load():
         "bftq_signature_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_signature_verify_with_cert_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_signature_signers": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u32p]),
+        "bftq_aggregator_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+        "bftq_aggregator_destroy": (None, [vp]),
+        "bftq_aggregator_verify": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64]),
+        "bftq_aggregator_stats": (C.c_int, [vp, u64p, u64p]),
         "bftq_collective_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_collective_combine_sufficient": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_int32)]),
         "bftq_graph_create": (C.c_int, [C.POINTER(vp)]),

@@ -152,6 +152,39 @@ class Signature:
         return [int(x) for x in out[:n.value]]
 
 
+class BatchingSignature:
+    """crypto.Signature whose single-item Verify calls, issued concurrently from many threads (bftkv:
+    goroutines), are coalesced into GPU batches by libbftq's aggregator (bftq_aggregator_*)."""
+
+    def __init__(self, keyring: Keyring, max_batch: int = 16384, max_wait_us: int = 200):
+        self.keyring, self._lib = keyring, _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.bftq_aggregator_create(keyring._h, max_batch, max_wait_us, C.byref(h)))
+        self._h = h
+
+    def _call(self, tbs: bytes, sig: bytes, cert: bytes):
+        rc = self._lib.bftq_aggregator_verify(self._h, tbs, len(tbs), sig, len(sig), cert or None, len(cert or b""))
+        if rc not in _ERR:
+            _lib.check(rc)
+        return _ERR[rc]
+
+    def verify(self, tbs: bytes, sig_data: bytes) -> Optional[str]:
+        return self._call(tbs, sig_data, b"")
+
+    def verify_with_certificate(self, tbs: bytes, sig_data: bytes, cert: bytes) -> Optional[str]:
+        return self._call(tbs, sig_data, cert)
+
+    def stats(self):
+        b, n = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.bftq_aggregator_stats(self._h, C.byref(b), C.byref(n)))
+        return {"batches": b.value, "items": n.value}
+
+    def close(self):
+        if self._h:
+            self._lib.bftq_aggregator_destroy(self._h)
+            self._h = None
+
+
 class CollectiveSignature:
     """crypto.CollectiveSignature (crypto_pgp.go:485-515)."""
 

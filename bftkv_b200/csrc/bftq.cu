@@ -16,7 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <map>
+#include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -240,7 +244,8 @@ int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_s
   const bool use32 = kb == 256 && (e->rsa_kernel == 32 || (e->rsa_kernel == 0 && e->all_2048));
   if (use32) {
     if (!e->all_2048) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a registered modulus is not 2048 bits");
-    auto kern = bftq::r32::rsa_verify_r32_kernel<128, 4>;
+    static const int min_blocks = [] { const char* v = getenv("BFTQ_R32_BLOCKS"); return v ? atoi(v) : 4; }();
+    auto kern = min_blocks == 5 ? bftq::r32::rsa_verify_r32_kernel<128, 5> : (min_blocks == 3 ? bftq::r32::rsa_verify_r32_kernel<128, 3> : bftq::r32::rsa_verify_r32_kernel<128, 4>);
     static thread_local int occ32 = 0;
     if (!occ32) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, kern, 128, 0)); if (occ32 < 1) occ32 = 1; }
     const uint64_t per_block = 4 * 8;
@@ -1375,6 +1380,104 @@ int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qc
   rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
   if (rc) return rc;
   *out = (bits[0] & BFTQ_TALLY_IS_SUFFICIENT) ? 1 : 0;
+  return BFTQ_OK;
+}
+
+// ---- batching aggregator ------------------------------------------------------------------------
+}  // extern "C"
+
+struct bftq_aggregator {
+  struct Job {
+    std::vector<uint8_t> tbs, sig, cert;
+    int result = 0;
+    bool done = false;
+  };
+  bftq_keyring* kr = nullptr;
+  uint32_t max_batch = 16384, max_wait_us = 200;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::vector<std::shared_ptr<Job>> queue;
+  std::chrono::steady_clock::time_point first_at;
+  bool stop = false;
+  uint64_t n_batches = 0, n_items = 0;
+  std::thread worker;
+
+  void flush(std::vector<std::shared_ptr<Job>>& batch) {
+    // split into plain and with-certificate halves, one packer call each
+    for (int with_cert = 0; with_cert < 2; with_cert++) {
+      std::vector<Job*> sel;
+      for (auto& j : batch) if ((j->cert.empty() ? 0 : 1) == with_cert) sel.push_back(j.get());
+      if (sel.empty()) continue;
+      std::vector<uint8_t> tb, sb, cb;
+      std::vector<uint64_t> to{0}, so{0}, co{0};
+      for (Job* j : sel) {
+        tb.insert(tb.end(), j->tbs.begin(), j->tbs.end()); to.push_back(tb.size());
+        sb.insert(sb.end(), j->sig.begin(), j->sig.end()); so.push_back(sb.size());
+        cb.insert(cb.end(), j->cert.begin(), j->cert.end()); co.push_back(cb.size());
+      }
+      std::vector<int32_t> err(sel.size(), BFTQ_ERR_INVALID_SIGNATURE);
+      int rc = with_cert ? bftq_signature_verify_with_cert_batch(kr, tb.data(), to.data(), sb.data(), so.data(), cb.data(), co.data(), sel.size(), err.data())
+                         : bftq_signature_verify_batch(kr, tb.data(), to.data(), sb.data(), so.data(), sel.size(), err.data());
+      for (size_t i = 0; i < sel.size(); i++) sel[i]->result = rc ? rc : err[i];
+    }
+  }
+  void loop() {
+    std::unique_lock<std::mutex> l(mu);
+    for (;;) {
+      cv_work.wait(l, [&] { return stop || !queue.empty(); });
+      if (stop && queue.empty()) return;
+      // wait for the batch to fill up or its deadline to pass
+      const auto deadline = first_at + std::chrono::microseconds(max_wait_us);
+      cv_work.wait_until(l, deadline, [&] { return stop || queue.size() >= max_batch; });
+      std::vector<std::shared_ptr<Job>> batch;
+      batch.swap(queue);
+      l.unlock();
+      flush(batch);
+      l.lock();
+      for (auto& j : batch) j->done = true;
+      n_batches += 1;
+      n_items += batch.size();
+      cv_done.notify_all();
+    }
+  }
+};
+
+extern "C" {
+
+int bftq_aggregator_create(bftq_keyring* kr, uint32_t max_batch, uint32_t max_wait_us, bftq_aggregator** out) {
+  if (!kr || !out || max_batch == 0) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  auto* a = new bftq_aggregator();
+  a->kr = kr; a->max_batch = max_batch; a->max_wait_us = max_wait_us;
+  a->worker = std::thread([a] { a->loop(); });
+  *out = a;
+  return BFTQ_OK;
+}
+void bftq_aggregator_destroy(bftq_aggregator* a) {
+  if (!a) return;
+  { std::lock_guard<std::mutex> l(a->mu); a->stop = true; }
+  a->cv_work.notify_all();
+  a->worker.join();
+  delete a;
+}
+int bftq_aggregator_verify(bftq_aggregator* a, const uint8_t* tbs, uint64_t tbs_len, const uint8_t* sig, uint64_t sig_len,
+                           const uint8_t* cert, uint64_t cert_len) {
+  if (!a || (tbs_len && !tbs) || (sig_len && !sig) || (cert_len && !cert)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  auto j = std::make_shared<bftq_aggregator::Job>();
+  j->tbs.assign(tbs, tbs + tbs_len); j->sig.assign(sig, sig + sig_len);
+  if (cert_len) j->cert.assign(cert, cert + cert_len);
+  std::unique_lock<std::mutex> l(a->mu);
+  if (a->stop) return fail(BFTQ_ERR_INVALID_ARG, "aggregator is shutting down");
+  if (a->queue.empty()) a->first_at = std::chrono::steady_clock::now();
+  a->queue.push_back(j);
+  a->cv_work.notify_all();
+  a->cv_done.wait(l, [&] { return j->done; });
+  return j->result;
+}
+int bftq_aggregator_stats(bftq_aggregator* a, uint64_t* n_batches, uint64_t* n_items) {
+  if (!a) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(a->mu);
+  if (n_batches) *n_batches = a->n_batches;
+  if (n_items) *n_items = a->n_items;
   return BFTQ_OK;
 }
 

@@ -276,6 +276,21 @@ int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_b
  * issuers present in the keyring (primary ids via getCertById), duplicates kept, in packet order. */
 int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n);
 
+/* Batching aggregator: bftkv calls Signature.Verify one (tbs, sig) at a time from many goroutines
+ * (one per peer in transport.Multicast, transport/transport.go:110-127; one per HTTP request on the
+ * servers).  bftq_aggregator_verify blocks its caller until the batch it was coalesced into has been
+ * verified: a batch is flushed when it reaches max_batch items or max_wait_us after its first item.
+ * This is where "tens of thousands of tuples" come from without touching bftkv's call sites.
+ * cert / cert_len may be NULL / 0 (Verify) or carry the issuer's key block (VerifyWithCertificate).
+ * Returns 0 (valid), BFTQ_ERR_INVALID_SIGNATURE, or a BFTQ_ERR_* infrastructure error. */
+typedef struct bftq_aggregator bftq_aggregator;
+int  bftq_aggregator_create(bftq_keyring* kr, uint32_t max_batch, uint32_t max_wait_us, bftq_aggregator** out);
+void bftq_aggregator_destroy(bftq_aggregator* a);
+int  bftq_aggregator_verify(bftq_aggregator* a, const uint8_t* tbs, uint64_t tbs_len, const uint8_t* sig, uint64_t sig_len,
+                            const uint8_t* cert, uint64_t cert_len);
+/* batches flushed / items verified since creation */
+int  bftq_aggregator_stats(bftq_aggregator* a, uint64_t* n_batches, uint64_t* n_items);
+
 /* Quorum descriptor by node id, for the collective-signature calls (members are node.Id()s). */
 typedef struct {
   int32_t f, min, threshold, suff;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from bftkv_b200 import Engine
-from bftkv_b200.crypto_gpu import (CollectiveSignature, ErrInsufficientNumberOfSignatures, ErrInvalidSignature, Keyring, Quorum,
+from bftkv_b200.crypto_gpu import (BatchingSignature, CollectiveSignature, ErrInsufficientNumberOfSignatures, ErrInvalidSignature, Keyring, Quorum,
                                    Signature)
 from oracle import packet_oracle as pk, pgp_oracle as pgp, wotqs_oracle as wq
 from oracle.wotqs_oracle import Node
@@ -122,3 +122,34 @@ def test_collective_signature(env, golden):
     assert q.is_threshold(clique[:3]) and not q.is_threshold(clique[:2]) and q.is_threshold([clique[0]] * 3)
     assert q.is_sufficient(clique[:3]) and q.is_quorum(clique) and not q.is_quorum(clique[:3])
     assert q.reject(clique[:2]) and not q.reject(clique[:1]) and q.get_threshold() == 3
+
+
+def test_aggregator_coalesces_concurrent_verifies(env, golden):
+    """64 threads x 8 single Verify calls (the goroutine-per-peer pattern of transport.Multicast) must
+    give the reference's answers and end up in far fewer GPU batches than calls."""
+    import threading
+    cases = [c for c in golden["cases"] if c["hash"] == "SHA256"]
+    bs = BatchingSignature(env["kr"], max_batch=256, max_wait_us=20000)
+    results = {}
+
+    def worker(t):
+        for i in range(8):
+            c = cases[(t * 8 + i) % len(cases)]
+            tamper = (t + i) % 3 == 0
+            tbs = bytes.fromhex(c["tbs"]) + (b"!" if tamper else b"")
+            if i % 4 == 3:
+                cert = bytes.fromhex(golden["keys"][c["signer"]]["pub"])
+                got = bs.verify_with_certificate(tbs, bytes.fromhex(c["sig"]), cert)
+                ref = pgp.signature_verify_with_certificate(cert, tbs, bytes.fromhex(c["sig"]))
+            else:
+                got = bs.verify(tbs, bytes.fromhex(c["sig"]))
+                ref = pgp.signature_verify(env["ents"], tbs, bytes.fromhex(c["sig"]))
+            results[(t, i)] = (got, ref)
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(64)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert len(results) == 512 and all(g == r for g, r in results.values())
+    assert sum(g is None for g, _ in results.values()) > 150
+    st = bs.stats()
+    assert st["items"] == 512 and st["batches"] <= 64, st
+    bs.close()
