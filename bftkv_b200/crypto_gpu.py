@@ -82,10 +82,11 @@ class Quorum:
 class Keyring:
     """crypto/pgp PGPKeyring (crypto_pgp.go:115-223) over bftq_keyring."""
 
-    def __init__(self, engine: Engine):
+    def __init__(self, engine: Optional[Engine]):
+        """engine=None gives a parse-only keyring (host side only: parse / signers / certifiers)."""
         self.engine, self._lib = engine, _lib.load()
         h = C.c_void_p()
-        _lib.check(self._lib.bftq_keyring_create(engine._h, C.byref(h)))
+        _lib.check(self._lib.bftq_keyring_create(engine._h if engine is not None else None, C.byref(h)))
         self._h = h
 
     def register(self, key_blocks: bytes, priv: bool = False) -> int:
@@ -142,6 +143,15 @@ class Signature:
 
     def verify_with_certificate(self, tbs: bytes, sig_data: bytes, cert: bytes) -> Optional[str]:
         return self.verify_batch([tbs], [sig_data], [cert])[0]
+
+    def parse(self, sig_data: bytes, collective: bool = False):
+        """Host-only walk of a SignaturePacket.Data stream: ([(issuer id, hash id), ...], failed)."""
+        buf = np.frombuffer(sig_data or b"\0", np.uint8).copy()
+        iss, hid = np.zeros(1024, np.uint64), np.zeros(1024, np.uint8)
+        n, failed = C.c_uint32(), C.c_int32()
+        _lib.check(self._lib.bftq_signature_parse(self.keyring._h, C.c_void_p(buf.ctypes.data), len(sig_data), int(collective),
+                                                  C.c_void_p(iss.ctypes.data), C.c_void_p(hid.ctypes.data), 1024, C.byref(n), C.byref(failed)))
+        return [(int(iss[i]), int(hid[i])) for i in range(min(n.value, 1024))], bool(failed.value)
 
     def signers(self, sig_data: bytes) -> List[int]:
         buf = np.frombuffer(sig_data or b"\0", np.uint8).copy()

@@ -838,6 +838,21 @@ int bftq_modexp_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, const 
   return a.download();
 }
 
+int bftq_modprod_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const uint8_t* vals_be, uint64_t n_items,
+                       uint8_t* out_be) {
+  if (!e || !m_be || !vals_be || !out_be || k == 0) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  uint8_t *d_v, *d_o;
+  a.in(&d_v, vals_be, (size_t)n_items * k * mlen);
+  a.out(&d_o, out_be, (size_t)n_items * mlen);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = modprod_any(e, m_be, mlen, d_v, k, n_items, d_o, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
 // prod_i Y_i^lambda_i mod p with lambda_i = Lagrange(x_i, xs, q): K3 (lambda) -> K5 modexp -> K5 product.
 static int lagrange_exp_product_dev(bftq_engine* e, Arena& a, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, uint32_t k,
                                     const int32_t* d_x, const uint8_t* d_y, uint64_t n_items, uint8_t* d_lambda, uint8_t* d_pow, uint8_t* d_dummy_out,
@@ -971,6 +986,7 @@ namespace pg = bftq::pgp;
 
 // Enter an RSA key in the engine's table (deduplicated).  Returns -1 when the size is not built.
 int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
+  if (!e) return -1;
   if (!(k.algo == 1 || k.algo == 2 || k.algo == 3)) return -1;
   if (!bftq::class_supported((int)(k.nbits + 7) / 8) || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
   std::string id((const char*)k.n_be.data(), k.n_be.size());
@@ -1168,7 +1184,7 @@ int check_blobs(const void* blob, const uint64_t* off, uint64_t n) {
 extern "C" {
 
 int bftq_keyring_create(bftq_engine* e, bftq_keyring** out) {
-  if (!e || !out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");      // e == NULL: parse-only keyring (no device, no verification)
   auto* kr = new bftq_keyring();
   kr->e = e;
   *out = kr;
@@ -1234,6 +1250,7 @@ static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const ui
                              const uint64_t* sig_off, const uint8_t* cert_blob, const uint64_t* cert_off, uint64_t n_items,
                              int32_t* out_err) {
   if (!kr || !out_err) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
   if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(sig_blob, sig_off, n_items) || (cert_off && check_blobs(cert_blob, cert_off, n_items)))
     return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
   if (n_items == 0) return BFTQ_OK;
@@ -1269,6 +1286,34 @@ static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const ui
     if (cert_off && cert_rings[i].empty()) ok = false;
     out_err[i] = ok ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
   }
+  return BFTQ_OK;
+}
+
+int bftq_signature_parse(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, int collective, uint64_t* out_issuers,
+                         uint8_t* out_hash_ids, uint32_t cap, uint32_t* n_calls, int32_t* failed) {
+  if (!kr || !n_calls || !failed || (sig_len && !sig)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<pg::Entity> sec, pub;
+  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
+  std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
+  pg::Reader r{sig, (size_t)sig_len, 0};
+  std::vector<uint8_t> scratch;
+  std::vector<pg::KeyRef> keys;
+  pg::SigPacket sp;
+  uint32_t calls = 0;
+  *failed = 0;
+  while (r.remaining() > 0) {
+    const int rc = pg::next_known_signature(r, rings, sp, keys, scratch);
+    if (rc == pg::kOk) {
+      if (calls < cap) { if (out_issuers) out_issuers[calls] = sp.issuer; if (out_hash_ids) out_hash_ids[calls] = sp.hash_id; }
+      calls++;
+    } else if (collective) {
+      continue;
+    } else {
+      *failed = 1;
+      break;
+    }
+  }
+  *n_calls = calls;
   return BFTQ_OK;
 }
 
@@ -1345,6 +1390,7 @@ int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uin
                                  uint32_t n_members, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* ss_blob,
                                  const uint64_t* ss_off, uint64_t n_items, int32_t* out_err) {
   if (!kr || !out_err || (n_qc && !qcs) || (n_members && !member_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
   if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(ss_blob, ss_off, n_items)) return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
   if (n_items == 0) return BFTQ_OK;
   std::vector<pg::Entity> sec, pub;
@@ -1373,6 +1419,7 @@ int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uin
 int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
                                        uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out) {
   if (!kr || !out || (ss_len && !ss)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: the sufficiency tally runs on the GPU");
   std::vector<std::vector<uint64_t>> signers(1);
   int rc = signers_impl(kr, ss, ss_len, signers[0]);
   if (rc) return rc;

@@ -172,6 +172,15 @@ class Engine:
         _lib.check(self._lib.bftq_modexp_batch(self._h, _ptr(mb), mlen, _ptr(bb), _ptr(eb), elen, n, _ptr(out)))
         return [int.from_bytes(bytes(o), "big") for o in out]
 
+    def modprod_batch(self, m: int, vals):
+        """Threshold-RSA combine: [prod(row) mod m for row in vals] (rows of equal length)."""
+        mlen = (m.bit_length() + 7) // 8
+        B, k = len(vals), len(vals[0])
+        mb, vb = self._be([m], mlen), self._be([v for row in vals for v in row], mlen)
+        out = np.empty((B, mlen), np.uint8)
+        _lib.check(self._lib.bftq_modprod_batch(self._h, _ptr(mb), mlen, k, _ptr(vb), B, _ptr(out)))
+        return [bytes(o) for o in out]
+
     def lagrange_exp_product_batch(self, p: int, q: int, x, ys):
         """auth.calculateSharedSecret: prod_j ys[i][j]^lambda_j mod p.  x: (B,k) ints, ys: B lists of k ints."""
         plen, qlen = (p.bit_length() + 7) // 8, (q.bit_length() + 7) // 8

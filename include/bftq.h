@@ -211,6 +211,11 @@ int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t ml
  * (mlen = 128 / 256); base: n_items x mlen, exp: n_items x elen bytes, all big-endian. */
 int bftq_modexp_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, const uint8_t* base_be, const uint8_t* exp_be,
                       uint32_t elen, uint64_t n_items, uint8_t* out_be);
+/* Threshold-RSA combine (crypto/threshold/rsa/rsa.go:244-251,318-329 calculateSignature): the product of the
+ * k partial signatures at the leaves of a completed signature tree, out[i] = prod_j vals[i][j] mod N, left-padded
+ * to len(N) like I2OS (rsa.go:380-393).  N: exactly 1024 or 2048 bits; vals: n_items x k x mlen. */
+int bftq_modprod_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const uint8_t* vals_be, uint64_t n_items,
+                       uint8_t* out_be);
 /* AuthClient.calculateSharedSecret (crypto/auth/auth.go:386-399) and the first half of CalculateR:
  * out[i] = prod_j y[i][j]^lambda_j mod p,  lambda_j = sss.Lagrange(x[i][j], x[i][*], q).
  * p: plen = 128/256 bytes; q: any odd modulus up to 256 bytes (auth uses q = (p-1)/2). */
@@ -290,6 +295,14 @@ int  bftq_aggregator_verify(bftq_aggregator* a, const uint8_t* tbs, uint64_t tbs
                             const uint8_t* cert, uint64_t cert_len);
 /* batches flushed / items verified since creation */
 int  bftq_aggregator_stats(bftq_aggregator* a, uint64_t* n_batches, uint64_t* n_items);
+
+/* Parse-only inspection of one SignaturePacket.Data stream against the keyring (host only, no GPU):
+ * how the reference's loop over openpgp.CheckDetachedSignature would walk it.  collective = 0:
+ * Signature.Verify's strict walk (stops at the first structural error / unknown-issuer tail, *failed = 1);
+ * collective != 0: CollectiveSignature.Verify's tolerant walk.  Writes, per call that reached a
+ * known-issuer signature packet, the issuer key id and the OpenPGP hash id (up to cap entries). */
+int bftq_signature_parse(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, int collective, uint64_t* out_issuers,
+                         uint8_t* out_hash_ids, uint32_t cap, uint32_t* n_calls, int32_t* failed);
 
 /* Quorum descriptor by node id, for the collective-signature calls (members are node.Id()s). */
 typedef struct {

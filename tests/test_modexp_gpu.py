@@ -72,3 +72,31 @@ def test_dsa_calculate_r(engine, golden):
         exp.append(r)
     got, st = engine.dsa_calculate_r_batch(p, q, np.array(xs, np.int32), ris, vis)
     assert not st.any() and got == exp
+
+
+def test_threshold_rsa_combine(engine):
+    """crypto/threshold/rsa: the signature is the product of the partial signatures m^{d_i} mod N over an
+    additive split of d (rsa.go:318-329; TestCombine rsa_test.go:165-206 checks it equals the plain
+    PKCS#1 v1.5 signature).  Product on the GPU (K5), result verified by K1."""
+    import hashlib
+    from bftkv_b200 import workload
+    rng = random.Random(3)
+    keys = workload.load_keys(3)
+    vals, exp, kidx, digs = [], [], [], []
+    for i in range(48):
+        key = keys[i % 3]
+        d = hashlib.sha256(b"tbs%d" % i).digest()
+        em = workload.em_for_digest(d)
+        parts = [rng.randrange(key["d"]) for _ in range(6)]
+        parts.append(key["d"] - sum(parts))                       # additive split; the last share may be negative
+        psigs = [pow(em, p, key["n"]) if p >= 0 else pow(pow(em, -p, key["n"]), -1, key["n"]) for p in parts]   # rsa.go:140-178
+        vals.append(psigs)
+        exp.append(pow(em, key["d"], key["n"]).to_bytes(256, "big"))
+        kidx.append(i % 3); digs.append(d)
+    for n_, rows in [(keys[j]["n"], [v for i, v in enumerate(vals) if i % 3 == j]) for j in range(3)]:
+        got = engine.modprod_batch(n_, rows)
+        assert got == [e for i, e in enumerate(exp) if keys[i % 3]["n"] == n_]
+    first = engine.register_rsa_keys([k["n"] for k in keys], [65537] * 3)
+    st = engine.rsa_verify_batch(np.array(kidx, np.uint32) + first, np.frombuffer(b"".join(exp), np.uint8).reshape(-1, 256).copy(),
+                                 np.frombuffer(b"".join(digs), np.uint8).reshape(-1, 32).copy())
+    assert not st.any()
