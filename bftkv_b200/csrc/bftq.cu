@@ -8,6 +8,7 @@
 #include "lagrange.cuh"
 #include "modexp.cuh"
 #include "ed25519.cuh"
+#include "p256.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
@@ -940,6 +941,48 @@ int bftq_dsa_calculate_r_batch(bftq_engine* e, const uint8_t* p_be, uint32_t ple
     std::lock_guard<std::mutex> g(e->mu);
     e->stats.launches += 2;
   }
+  return a.download();
+}
+
+int bftq_ecdsa_p256_calculate_r_batch(bftq_engine* e, uint32_t k, const int32_t* x, const uint8_t* ri, const uint8_t* vi_be,
+                                      uint64_t n_items, uint8_t* out_r_be, uint8_t* out_status) {
+  if (!e || !x || !ri || !vi_be || !out_r_be || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "k must be 1..255");
+  if (n_items == 0) return BFTQ_OK;
+  static const uint8_t kN[32] = {0xff, 0xff, 0xff, 0xff, 0x00, 0x00, 0x00, 0x00, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff,
+                                 0xbc, 0xe6, 0xfa, 0xad, 0xa7, 0x17, 0x9e, 0x84, 0xf3, 0xb9, 0xca, 0xc2, 0xfc, 0x63, 0x25, 0x51};
+  Arena a(e);
+  int32_t* d_x; uint8_t *d_ri, *d_vi, *d_lam, *d_tmp, *d_st, *d_st2, *d_v, *d_vinv, *d_ok, *d_out; uint32_t* d_jac;
+  a.in(&d_x, x, (size_t)n_items * k);
+  a.in(&d_ri, ri, (size_t)n_items * k * 65);
+  a.in(&d_vi, vi_be, (size_t)n_items * k * 32);
+  a.out(&d_lam, (uint8_t*)nullptr, (size_t)n_items * k * 32, 0);
+  a.out(&d_tmp, (uint8_t*)nullptr, (size_t)n_items * 32, 0);
+  a.out(&d_v, (uint8_t*)nullptr, (size_t)n_items * 32, 0);
+  a.out(&d_vinv, (uint8_t*)nullptr, (size_t)n_items * 32, 0);
+  a.out(&d_jac, (uint32_t*)nullptr, (size_t)n_items * k * 24, 0);
+  a.out(&d_ok, (uint8_t*)nullptr, (size_t)n_items * k, 0);
+  a.out(&d_st2, (uint8_t*)nullptr, (size_t)n_items, 0);
+  a.out(&d_st, out_status, (size_t)n_items);
+  a.out(&d_out, out_r_be, (size_t)n_items * 32);
+  int rc = a.upload();
+  if (rc) return rc;
+  cudaStream_t st = a.stream();
+  CU(cudaMemsetAsync(d_lam, 0, (size_t)n_items * k * 32, st));
+  rc = launch_lagrange_any(e, kN, 32, k, d_x, d_lam, n_items, d_tmp, d_st2, d_lam, st);          // lambda_i mod N
+  if (rc) return rc;
+  const int block = 128;
+  bftq::p256_scalar_mul_kernel<<<(unsigned)((n_items * k + block - 1) / block), block, 0, st>>>(d_ri, d_lam, n_items * k, d_jac, d_ok);
+  CU(cudaGetLastError());
+  rc = launch_lagrange_any(e, kN, 32, k, d_x, d_vi, n_items, d_v, d_st2, nullptr, st);             // v = sum v_i lambda_i
+  if (rc) return rc;
+  bftq::LagrangeMod<8> M;
+  make_lagrange_mod<8>(kN, 32, M);
+  bftq::fermat_inverse_kernel<8><<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(M, d_v, n_items, d_vinv, nullptr);
+  CU(cudaGetLastError());
+  bftq::p256_sum_mul_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(d_jac, d_ok, k, d_vinv, n_items, d_out, d_st);
+  CU(cudaGetLastError());
+  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 3; }
   return a.download();
 }
 

@@ -206,6 +206,16 @@ class Engine:
                                                         _ptr(x), _ptr(rb), _ptr(vb), B, _ptr(out), _ptr(st)))
         return [int.from_bytes(bytes(o), "big") for o in out], st
 
+    def ecdsa_p256_calculate_r_batch(self, x, ris, vis):
+        """ecdsa.CalculateR: x (B,k) ints, ris: B lists of k 65-byte uncompressed points, vis: B lists of k ints."""
+        x = np.ascontiguousarray(x, np.int32)
+        B, k = x.shape
+        rb = np.frombuffer(b"".join(p for row in ris for p in row), np.uint8).copy()
+        vb = self._be([v for row in vis for v in row], 32)
+        out, st = np.empty((B, 32), np.uint8), np.empty(B, np.uint8)
+        _lib.check(self._lib.bftq_ecdsa_p256_calculate_r_batch(self._h, k, _ptr(x), _ptr(rb), _ptr(vb), B, _ptr(out), _ptr(st)))
+        return [int.from_bytes(bytes(o), "big") for o in out], st
+
     # ---- K4 ----
     def pgp_digest_batch(self, datas, suffixes, data_idx=None, hash_alg=HASH_SHA256):
         """datas: list of bytes (TBS strings); suffixes: list of bytes (one per signature)."""

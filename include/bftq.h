@@ -230,6 +230,12 @@ int bftq_dsa_calculate_r_batch(bftq_engine* e, const uint8_t* p_be, uint32_t ple
                                const int32_t* x, const uint8_t* ri_be, const uint8_t* vi_be, uint64_t n_items,
                                uint8_t* out_r_be, uint8_t* out_status);
 
+/* ecdsaGroupOperations.CalculateR on P-256 (crypto/threshold/ecdsa/ecdsa.go:36-59):
+ * R = (sum_i lambda_i * R_i) * v^-1 with v = sum_i v_i lambda_i mod N, r = R.x mod N.
+ * ri: n_items x k x 65 bytes (elliptic.Marshal: 04 || X || Y), vi: n_items x k x 32, out_r: n_items x 32. */
+int bftq_ecdsa_p256_calculate_r_batch(bftq_engine* e, uint32_t k, const int32_t* x, const uint8_t* ri, const uint8_t* vi_be,
+                                      uint64_t n_items, uint8_t* out_r_be, uint8_t* out_status);
+
 /* ---- K4: batched OpenPGP v4 signature digest --------------------------------------------------
  * Replaces hashForSignature + the hash-suffix step of packet.PublicKey.VerifySignature
  * (x/crypto, reached from crypto_pgp.go:324,338,490): digest_i = H(data[data_idx[i]] || suffix_i).

@@ -102,3 +102,54 @@ def rsa_combine(psigs: Sequence[int], n: int) -> bytes:                    # rsa
     for p in psigs:
         s = (s * p) % n
     return i2os(s, (n.bit_length() + 7) // 8)
+
+
+# ---- P-256 (crypto/elliptic) and ecdsaGroupOperations.CalculateR ---------------------------------
+P256_P = 2 ** 256 - 2 ** 224 + 2 ** 192 + 2 ** 96 - 1
+P256_B = 0x5ac635d8aa3a93e7b3ebbd55769886bc651d06b0cc53b0f63bce3c3e27d2604b
+P256_N = 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551
+P256_G = (0x6b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296,
+          0x4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5)
+
+
+def p256_add(P, Q):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    p = P256_P
+    if P[0] == Q[0]:
+        if (P[1] + Q[1]) % p == 0:
+            return None
+        l = (3 * P[0] * P[0] - 3) * pow(2 * P[1], -1, p) % p
+    else:
+        l = (Q[1] - P[1]) * pow(Q[0] - P[0], -1, p) % p
+    x = (l * l - P[0] - Q[0]) % p
+    return x, (l * (P[0] - x) - P[1]) % p
+
+
+def p256_mul(k, P):
+    R = None
+    while k:
+        if k & 1:
+            R = p256_add(R, P)
+        P = p256_add(P, P)
+        k >>= 1
+    return R
+
+
+def p256_marshal(P) -> bytes:                       # elliptic.Marshal
+    return b"\x04" + P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big")
+
+
+def ecdsa_calculate_r(rs: Sequence[Tuple[int, Tuple[int, int], int]]) -> int:
+    """crypto/threshold/ecdsa/ecdsa.go:36-59.  rs: (x_i, R_i (affine point), v_i)."""
+    xs = [x for x, _, _ in rs]
+    acc, v = None, 0
+    for x, ri, vi in rs:
+        l = lagrange(x, xs, P256_N)
+        acc = p256_add(acc, p256_mul(l, ri))
+        v = (v + (vi * l) % P256_N) % P256_N
+    v = pow(v, -1, P256_N)
+    R = p256_mul(v, acc)
+    return R[0] % P256_N

@@ -1,0 +1,18 @@
+// Host build of bftkv_b200/csrc/p256.cuh (the same __host__ __device__ code the kernels run).
+#include "../../bftkv_b200/csrc/p256.cuh"
+using namespace bftq::p256;
+extern "C" {
+// out = k * P  (P: 65-byte uncompressed); returns 0 if P is not on the curve, 2 for infinity
+int p256_mul_host(const uint8_t* point, const uint8_t* k_be, uint8_t* out65) {
+  pt p; if (!pt_from_uncompressed(p, point)) return 0;
+  uint32_t k[8]; be_to_limbs(k, k_be);
+  pt r; pt_mul(r, p, k);
+  out65[0] = 4;
+  return pt_to_affine(out65 + 1, out65 + 33, r) ? 1 : 2;
+}
+int p256_add_host(const uint8_t* a, const uint8_t* b, uint8_t* out65) {
+  pt p, q; if (!pt_from_uncompressed(p, a) || !pt_from_uncompressed(q, b)) return 0;
+  pt r; pt_add(r, p, q); out65[0] = 4;
+  return pt_to_affine(out65 + 1, out65 + 33, r) ? 1 : 2;
+}
+}
