@@ -132,6 +132,8 @@ def run_gpu(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = workload.make_verify_batch(ITEMS, NKEYS, seed=0xBF7C0002 + rank, corrupt_seed=0xBF7C0003 + rank,
@@ -180,11 +182,11 @@ def run_gpu(args, rank, local_rank, world):
         assert np.array_equal(d_st[c].cpu().numpy(), w["expect"]), "device-resident results differ from expectation"
 
     # ---- end-to-end leg: pinned host buffers through the host C-ABI call ------------------------
-    # Two concurrent callers (bftkv calls the crypto layer from one goroutine per peer,
+    # NCALLERS concurrent callers (bftkv calls the crypto layer from one goroutine per peer,
     # transport/transport.go:110-127; the C ABI is re-entrant): while one call's kernel runs, the
     # other call's H2D copy is in flight.  Every step still copies its full inputs H2D and its
     # status bytes D2H inside the timed region.
-    NCALLERS = 2
+    NCALLERS = args.callers
     h_in = [(torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory(), torch.from_numpy(w["sig"]).pin_memory(),
              torch.from_numpy(w["digest"]).pin_memory(), torch.empty(ITEMS, dtype=torch.uint8).pin_memory()) for _ in range(NCALLERS)]
     for c in range(NCALLERS):
@@ -371,6 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--copies", type=int, default=8)
+    ap.add_argument("--callers", type=int, default=2, help="concurrent host callers in the end-to-end leg")
     ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
