@@ -9,6 +9,7 @@
 #include "modexp.cuh"
 #include "ed25519.cuh"
 #include "p256.cuh"
+#include "dsa_verify.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
@@ -20,6 +21,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <map>
+#include <tuple>
 #include <memory>
 #include <thread>
 #include <mutex>
@@ -112,6 +114,9 @@ struct bftq_engine {
   std::vector<StagingSlot*> slots;
   bftq_stats_t stats{};
   std::map<std::string, uint32_t> key_lookup;   // (modulus bytes || e) -> key table index
+  struct DsaKey { std::vector<uint8_t> p, q, gy; int cls; };   // gy: g || y, each padded to |p| bytes
+  std::vector<DsaKey> dsa_keys;                  // host table; a group's domain travels with its launch
+  std::map<std::string, uint32_t> dsa_lookup;
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
@@ -513,6 +518,35 @@ int bftq_ed25519_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n
   return a.download();
 }
 
+// ---- K1c --------------------------------------------------------------------------------------
+int bftq_ecdsa_p256_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* key_idx,
+                                 const uint8_t* r_be, const uint8_t* s_be, const uint8_t* digest, uint32_t digest_len,
+                                 uint64_t n_items, uint8_t* out_status) {
+  if (!e || !pubkeys || !key_idx || !r_be || !s_be || !digest || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (digest_len == 0 || digest_len > 64) return fail(BFTQ_ERR_INVALID_ARG, "digest_len must be 1..64");
+  if (n_items == 0) return BFTQ_OK;
+  Arena a(e);
+  uint8_t *d_pk, *d_r, *d_s, *d_dg, *d_st; uint32_t* d_idx;
+  a.in(&d_pk, pubkeys, (size_t)std::max<uint32_t>(n_keys, 1) * 64, (size_t)n_keys * 64);
+  a.in(&d_idx, key_idx, (size_t)n_items);
+  a.in(&d_r, r_be, (size_t)n_items * 32);
+  a.in(&d_s, s_be, (size_t)n_items * 32);
+  a.in(&d_dg, digest, (size_t)n_items * digest_len);
+  a.out(&d_st, out_status, (size_t)n_items);
+  int rc = a.upload();
+  if (rc) return rc;
+  const int block = 128;
+  bftq::ecdsa_p256_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, a.stream()>>>(
+      d_pk, n_keys, d_idx, d_r, d_s, d_dg, digest_len, n_items, nullptr, d_st);
+  CU(cudaGetLastError());
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    e->stats.launches += 1;
+    e->stats.items += n_items;
+  }
+  return a.download();
+}
+
 // ---- K2 ---------------------------------------------------------------------------------------
 }  // extern "C"
 
@@ -762,14 +796,14 @@ int make_moddev(const uint8_t* p_be, uint32_t plen, bftq::ModDev<W>& M) {
 }
 template <int W>
 int launch_modexp(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_base, const uint8_t* d_exp, uint32_t elen, uint64_t n,
-                  uint8_t* d_out, cudaStream_t st) {
+                  uint8_t* d_out, cudaStream_t st, uint32_t n_bases = 0) {
   bftq::ModDev<W> M;
   int rc = make_moddev<W>(p_be, plen, M);
   if (rc) return rc;
   const uint64_t per_block = 4 * 8;
   uint64_t grid = std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t)e->sm_count * 4);
   if (grid < 1) grid = 1;
-  bftq::modexp_kernel<W, 128><<<(unsigned)grid, 128, 0, st>>>(M, d_base, d_exp, elen, n, d_out);
+  bftq::modexp_kernel<W, 128><<<(unsigned)grid, 128, 0, st>>>(M, d_base, d_exp, elen, n, d_out, n_bases);
   CU(cudaGetLastError());
   { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
   return BFTQ_OK;
@@ -788,9 +822,9 @@ int launch_modprod(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uin
   return BFTQ_OK;
 }
 int modexp_any(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_base, const uint8_t* d_exp, uint32_t elen, uint64_t n,
-               uint8_t* d_out, cudaStream_t st) {
-  if (plen == 128) return launch_modexp<8>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st);
-  if (plen == 256) return launch_modexp<16>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st);
+               uint8_t* d_out, cudaStream_t st, uint32_t n_bases = 0) {
+  if (plen == 128) return launch_modexp<8>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st, n_bases);
+  if (plen == 256) return launch_modexp<16>(e, p_be, plen, d_base, d_exp, elen, n, d_out, st, n_bases);
   return fail(BFTQ_ERR_UNSUPPORTED_KEY, "exponentiation modulus must be 128 or 256 bytes (1024 / 2048 bit)");
 }
 int modprod_any(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* d_vals, uint32_t k, uint64_t n, uint8_t* d_out, cudaStream_t st) {
@@ -986,6 +1020,71 @@ int bftq_ecdsa_p256_calculate_r_batch(bftq_engine* e, uint32_t k, const int32_t*
   return a.download();
 }
 
+// ---- K1d: DSA verify ----------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+// Domain check for one DSA key: p odd with exactly 1024 / 2048 bits (K5's classes), q odd, at most 256 bits.
+// Returns 0 usable, 1 dsa.Verify is false for every signature (q's bit length is not a multiple of 8), 2 not built.
+int dsa_key_class(const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen) {
+  if (!(plen == 128 || plen == 256) || qlen == 0 || qlen > 32) return 2;
+  if (!(p_be[0] & 0x80) || !(p_be[plen - 1] & 1) || !(q_be[qlen - 1] & 1)) return 2;
+  if (!(q_be[0] & 0x80)) return q_be[0] == 0 ? 2 : 1;
+  return 0;
+}
+// d_r / d_s: 32-byte right-aligned values `stride` apart; d_bases: g || y (2 x plen); scratch: d_u (2n x qlen),
+// d_pow (2n x plen), d_prod (n x plen).  d_pre may be NULL.
+int dsa_verify_dev(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, const uint8_t* d_bases,
+                   const uint8_t* d_r, const uint8_t* d_s, uint32_t stride, const uint8_t* d_dig, uint32_t dlen, uint64_t n,
+                   const uint8_t* d_pre, uint8_t* d_u, uint8_t* d_pow, uint8_t* d_prod, uint8_t* d_st, cudaStream_t st) {
+  bftq::LagrangeMod<8> M;
+  make_lagrange_mod<8>(q_be, qlen, M);
+  const int block = 128;
+  const unsigned grid = (unsigned)((n + block - 1) / block);
+  bftq::dsa_prepare_kernel<8><<<grid, block, 0, st>>>(M, d_r, d_s, stride, d_dig, dlen, n, d_pre, d_u, d_st);
+  CU(cudaGetLastError());
+  int rc = modexp_any(e, p_be, plen, d_bases, d_u, qlen, 2 * n, d_pow, st, 2);
+  if (rc) return rc;
+  rc = modprod_any(e, p_be, plen, d_pow, 2, n, d_prod, st);
+  if (rc) return rc;
+  bftq::dsa_finish_kernel<8><<<grid, block, 0, st>>>(M, d_prod, plen, d_r, stride, n, d_st);
+  CU(cudaGetLastError());
+  std::lock_guard<std::mutex> g(e->mu);
+  e->stats.launches += 2;
+  e->stats.items += n;
+  return BFTQ_OK;
+}
+}  // namespace
+extern "C" {
+
+int bftq_dsa_verify_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, const uint8_t* g_be,
+                          const uint8_t* y_be, const uint8_t* r_be, const uint8_t* s_be, const uint8_t* digest, uint32_t digest_len,
+                          uint64_t n_items, uint8_t* out_status) {
+  if (!e || !p_be || !q_be || !g_be || !y_be || !r_be || !s_be || !digest || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (digest_len == 0 || digest_len > 64) return fail(BFTQ_ERR_INVALID_ARG, "digest_len must be 1..64");
+  const int cls = dsa_key_class(p_be, plen, q_be, qlen);
+  if (cls == 2) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "DSA domain: p must be odd with exactly 1024 / 2048 bits in plen bytes, q odd of at most 256 bits");
+  if (n_items == 0) return BFTQ_OK;
+  if (cls == 1) { memset(out_status, BFTQ_ST_BAD_SIGNATURE, (size_t)n_items); return BFTQ_OK; }   // dsa.Verify: q.BitLen() & 7 != 0
+  std::vector<uint8_t> bases(2 * (size_t)plen);
+  memcpy(bases.data(), g_be, plen);
+  memcpy(bases.data() + plen, y_be, plen);
+  Arena a(e);
+  uint8_t *d_b, *d_r, *d_s, *d_dg, *d_u, *d_pow, *d_prod, *d_st;
+  a.in(&d_b, bases.data(), bases.size());
+  a.in(&d_r, r_be, (size_t)n_items * 32);
+  a.in(&d_s, s_be, (size_t)n_items * 32);
+  a.in(&d_dg, digest, (size_t)n_items * digest_len);
+  a.out(&d_u, (uint8_t*)nullptr, 2 * (size_t)n_items * qlen, 0);
+  a.out(&d_pow, (uint8_t*)nullptr, 2 * (size_t)n_items * plen, 0);
+  a.out(&d_prod, (uint8_t*)nullptr, (size_t)n_items * plen, 0);
+  a.out(&d_st, out_status, (size_t)n_items);
+  int rc = a.upload();
+  if (rc) return rc;
+  rc = dsa_verify_dev(e, p_be, plen, q_be, qlen, d_b, d_r, d_s, 32, d_dg, digest_len, n_items, nullptr, d_u, d_pow, d_prod, d_st, a.stream());
+  if (rc) return rc;
+  return a.download();
+}
+
 // ---- K4 ---------------------------------------------------------------------------------------
 int bftq_pgp_digest_batch(bftq_engine* e, const uint8_t* data_blob, const uint64_t* data_off, uint32_t n_data,
                           const uint32_t* data_idx, const uint8_t* suffix_blob, const uint64_t* suffix_off,
@@ -1048,9 +1147,34 @@ int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
   e->key_lookup[id] = first;
   return (int32_t)first;
 }
+int32_t dsa_key_index(bftq_engine* e, const pg::PubKey& k) {
+  const auto &P = k.dsa[0], &Q = k.dsa[1], &G = k.dsa[2], &Y = k.dsa[3];
+  if (P.empty() || Q.empty() || G.size() > P.size() || Y.size() > P.size()) return -1;
+  const int cls = dsa_key_class(P.data(), (uint32_t)P.size(), Q.data(), (uint32_t)Q.size());
+  if (cls == 2) return -1;
+  std::string id;
+  for (int i = 0; i < 4; i++) { id.append((const char*)k.dsa[i].data(), k.dsa[i].size()); id.push_back((char)0xff); id.push_back((char)i); }
+  std::lock_guard<std::mutex> g(e->mu);
+  auto it = e->dsa_lookup.find(id);
+  if (it != e->dsa_lookup.end()) return (int32_t)it->second;
+  bftq_engine::DsaKey dk;
+  dk.p = P; dk.q = Q; dk.cls = cls;
+  dk.gy.assign(2 * P.size(), 0);
+  memcpy(dk.gy.data() + P.size() - G.size(), G.data(), G.size());
+  memcpy(dk.gy.data() + 2 * P.size() - Y.size(), Y.data(), Y.size());
+  e->dsa_keys.push_back(dk);
+  e->dsa_lookup[id] = (uint32_t)e->dsa_keys.size() - 1;
+  return (int32_t)e->dsa_keys.size() - 1;
+}
+int32_t any_key_index(bftq_engine* e, const pg::PubKey& k) {
+  if (!e) return -1;
+  if (k.algo == 19) return k.ec_xy.size() == 64 ? 0 : -1;       // P-256 keys travel with their tuples, no table
+  if (k.algo == 17) return dsa_key_index(e, k);
+  return engine_key_index(e, k);
+}
 void index_entity_keys(bftq_engine* e, pg::Entity& ent) {
-  ent.primary.table_idx = engine_key_index(e, ent.primary);
-  for (auto& sk : ent.subkeys) sk.key.table_idx = engine_key_index(e, sk.key);
+  ent.primary.table_idx = any_key_index(e, ent.primary);
+  for (auto& sk : ent.subkeys) sk.key.table_idx = any_key_index(e, sk.key);
 }
 
 struct Tuple {
@@ -1059,11 +1183,12 @@ struct Tuple {
   uint64_t signer_id;          // primary key id of the candidate key's entity
   uint8_t pre;                 // status decided on the host (0 = ask the GPU)
   uint8_t hash_id;
-  uint16_t kbytes;             // key-size class of the candidate key (signature is padded to it)
+  uint8_t alg;                 // 1: RSA (K1), 19: ECDSA P-256 (K1c), 17: DSA (K1d)
+  uint32_t kbytes;             // RSA: key-size class of the candidate key (signature is padded to it); DSA: key table index
   uint16_t tag;
   uint32_t data_idx;
   uint32_t suffix_pos, suffix_len;   // into suffix blob
-  uint8_t sig[512];
+  uint8_t sig[512];            // RSA: signature padded to kbytes.  ECDSA: r (32) || s (32) || X (32) || Y (32).  DSA: r (32) || s (32)
 };
 struct Plan {
   std::vector<Tuple> tuples;
@@ -1114,7 +1239,7 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
         }
         didx = (uint32_t)data_text;
       } else if (sp.sig_type != 0x00) common_pre = BFTQ_ST_BAD_SIGNATURE;       // hashForSignature: unsupported type
-      if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3)) common_pre = BFTQ_ST_UNSUPPORTED;   // DSA / ECDSA: not built
+      if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3 || sp.pk_algo == 17 || sp.pk_algo == 19)) common_pre = BFTQ_ST_UNSUPPORTED;
       if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // MD5 / RIPEMD-160: not built
       for (const pg::KeyRef& kr : keys) {
         Tuple t;
@@ -1128,6 +1253,28 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
         if (!t.pre && kr.key->algo != sp.pk_algo) t.pre = BFTQ_ST_BAD_SIGNATURE;   // "different algorithms"
         if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
         if (t.key_idx < 0) t.key_idx = 0;
+        t.alg = 1;
+        if (sp.pk_algo == 19 && kr.key->algo == 19) {                               // ecdsa.Verify: r, s >= N (any longer than 32 bytes) fail
+          t.alg = 19; t.kbytes = 0;
+          if (sp.r.size() > 32 || sp.s.size() > 32) { if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE; }
+          else {
+            memcpy(t.sig + 32 - sp.r.size(), sp.r.data(), sp.r.size());
+            memcpy(t.sig + 64 - sp.s.size(), sp.s.data(), sp.s.size());
+          }
+          if (kr.key->ec_xy.size() == 64) memcpy(t.sig + 64, kr.key->ec_xy.data(), 64);
+          pl.tuples.push_back(t);
+          continue;
+        }
+        if (sp.pk_algo == 17 && kr.key->algo == 17) {                               // dsa.Verify: r, s >= q (q <= 256 bits) fail
+          t.alg = 17; t.kbytes = (uint32_t)t.key_idx;
+          if (sp.r.size() > 32 || sp.s.size() > 32) { if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE; }
+          else {
+            memcpy(t.sig + 32 - sp.r.size(), sp.r.data(), sp.r.size());
+            memcpy(t.sig + 64 - sp.s.size(), sp.s.data(), sp.s.size());
+          }
+          pl.tuples.push_back(t);
+          continue;
+        }
         const size_t kb = (kr.key->nbits + 7) / 8;                                  // pub.Size()
         t.kbytes = (uint16_t)(bftq::class_supported((int)kb) ? kb : 256);
         if (sp.mpi.size() <= t.kbytes) memcpy(t.sig + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size());   // padToKeySize
@@ -1148,7 +1295,10 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
 
 // digest (K4) -> tag check -> RSA verify (K1) for every tuple of the plan; tuples are grouped by hash
 // algorithm (digest length differs), each group is one K4 + one K1 launch on one stream.
-int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, int kb, std::vector<uint8_t>& status) {
+int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, int alg, int kb, std::vector<uint8_t>& status) {
+  const uint32_t dsa_idx = (uint32_t)kb;
+  if (alg == 19) kb = 128;                                   // r || s || X || Y
+  if (alg == 17) kb = 64;                                    // r || s
   const size_t nt = sel.size();
   const int dlen = bftq::host_hash_dlen(hash_alg);
   std::vector<uint32_t> key_idx(nt), data_idx(nt);
@@ -1164,7 +1314,7 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
     sblob.insert(sblob.end(), pl.suffix_blob.begin() + t.suffix_pos, pl.suffix_blob.begin() + t.suffix_pos + t.suffix_len);
   }
   soff[nt] = sblob.size();
-  if (!e->d_keys || !bftq::digest_on_device(hash_alg)) {   // nothing verifiable: every tuple keeps its host status
+  if ((alg == 1 && !e->d_keys) || !bftq::digest_on_device(hash_alg)) {   // nothing verifiable: every tuple keeps its host status
     for (size_t i = 0; i < nt; i++) status[sel[i]] = pre[i] ? pre[i] : (uint8_t)BFTQ_ST_UNSUPPORTED;
     return BFTQ_OK;
   }
@@ -1180,13 +1330,40 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
   a.in(&d_pre, pre.data(), nt);
   a.in(&d_sig, sigs.data(), nt * (size_t)kb);
   a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
+  bftq_engine::DsaKey dk;
+  uint8_t *d_gy = nullptr, *d_u = nullptr, *d_pow = nullptr, *d_prod = nullptr;
+  if (alg == 17) {
+    { std::lock_guard<std::mutex> g(e->mu); if (dsa_idx < e->dsa_keys.size()) dk = e->dsa_keys[dsa_idx]; }
+    if (dk.p.empty() || dk.cls != 0) {                     // q's bit length not a multiple of 8: dsa.Verify is false
+      for (size_t i = 0; i < nt; i++) status[sel[i]] = pre[i] ? pre[i] : (uint8_t)(dk.p.empty() ? BFTQ_ST_UNSUPPORTED : BFTQ_ST_BAD_SIGNATURE);
+      return BFTQ_OK;
+    }
+    a.in(&d_gy, dk.gy.data(), dk.gy.size());
+    a.out(&d_u, (uint8_t*)nullptr, 2 * nt * dk.q.size(), 0);
+    a.out(&d_pow, (uint8_t*)nullptr, 2 * nt * dk.p.size(), 0);
+    a.out(&d_prod, (uint8_t*)nullptr, nt * dk.p.size(), 0);
+  }
   a.out(&d_st, st.data(), nt);
   int rc = a.upload();
   if (rc) return rc;
   CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, nt, d_dig, d_tags, d_pre, a.stream()));
   { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
-  rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream(), kb);
-  if (rc) return rc;
+  if (alg == 19) {
+    const int block = 128;
+    bftq::ecdsa_p256_verify_kernel<<<(unsigned)((nt + block - 1) / block), block, 0, a.stream()>>>(
+        d_sig, 0, nullptr, d_sig, d_sig + 32, d_dig, (uint32_t)dlen, nt, d_pre, d_st);
+    CU(cudaGetLastError());
+    std::lock_guard<std::mutex> g(e->mu);
+    e->stats.launches += 1;
+    e->stats.items += nt;
+  } else if (alg == 17) {
+    rc = dsa_verify_dev(e, dk.p.data(), (uint32_t)dk.p.size(), dk.q.data(), (uint32_t)dk.q.size(), d_gy, d_sig, d_sig + 32, 64, d_dig,
+                        (uint32_t)dlen, nt, d_pre, d_u, d_pow, d_prod, d_st, a.stream());
+    if (rc) return rc;
+  } else {
+    rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream(), kb);
+    if (rc) return rc;
+  }
   rc = a.download();
   if (rc) return rc;
   for (size_t i = 0; i < nt; i++) status[sel[i]] = st[i];
@@ -1195,10 +1372,11 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
 
 int run_plan(bftq_engine* e, Plan& pl, std::vector<uint8_t>& status) {
   status.assign(pl.tuples.size(), 0);
-  std::map<std::pair<uint32_t, int>, std::vector<uint32_t>> groups;    // (hash algorithm, key-size class)
-  for (size_t i = 0; i < pl.tuples.size(); i++) groups[{pl.tuples[i].hash_id, (int)pl.tuples[i].kbytes}].push_back((uint32_t)i);
+  std::map<std::tuple<uint32_t, int, int>, std::vector<uint32_t>> groups;    // (hash algorithm, signature algorithm, key-size class)
+  for (size_t i = 0; i < pl.tuples.size(); i++)
+    groups[std::make_tuple((uint32_t)pl.tuples[i].hash_id, (int)pl.tuples[i].alg, (int)pl.tuples[i].kbytes)].push_back((uint32_t)i);
   for (auto& g : groups) {
-    int rc = run_plan_group(e, pl, g.second, g.first.first, g.first.second, status);
+    int rc = run_plan_group(e, pl, g.second, std::get<0>(g.first), std::get<1>(g.first), std::get<2>(g.first), status);
     if (rc) return rc;
   }
   return BFTQ_OK;

@@ -42,7 +42,7 @@ __device__ __forceinline__ void store_be(uint8_t* p, int nbytes, const uint32_t 
 template <int W, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 modexp_kernel(const ModDev<W> M, const uint8_t* __restrict__ base_be, const uint8_t* __restrict__ exp_be, const uint32_t elen,
-              const uint64_t n_items, uint8_t* __restrict__ out_be) {
+              const uint64_t n_items, uint8_t* __restrict__ out_be, const uint32_t n_bases = 0) {
   using namespace r32;
   const int lane = threadIdx.x & 31;
   const int r = lane & (T - 1);
@@ -57,7 +57,7 @@ modexp_kernel(const ModDev<W> M, const uint8_t* __restrict__ base_be, const uint
     const uint64_t item_raw = wbase + (uint64_t)(lane / T);
     const bool valid = item_raw < n_items;
     const uint64_t item = valid ? item_raw : (n_items - 1);
-    const uint8_t* bp = base_be + item * (uint64_t)nbytes;
+    const uint8_t* bp = base_be + (n_bases ? item % n_bases : item) * (uint64_t)nbytes;   // n_bases > 0: shared bases, round robin
     const uint8_t* ep = exp_be + item * (uint64_t)elen;
     uint32_t xm[W], y[W], t[W];
     {

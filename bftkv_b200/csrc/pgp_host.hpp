@@ -94,6 +94,7 @@ struct SigPacket {
   uint8_t hash_tag[2] = {0, 0};
   std::vector<uint8_t> suffix;            // bytes hashed after the data (incl. trailer)
   std::vector<uint8_t> mpi;               // RSA signature MPI bytes (leading zeros stripped as stored)
+  std::vector<uint8_t> r, s;              // DSA / ECDSA signature MPIs, leading zeros stripped
 };
 
 inline int parse_subpackets(const uint8_t* a, size_t n, SigPacket& s, bool hashed) {
@@ -181,7 +182,13 @@ inline int parse_signature(const uint8_t* b, size_t n, SigPacket& s) {
   const uint8_t* md; size_t ml; unsigned bits;
   if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
   if (s.pk_algo == 1 || s.pk_algo == 3) s.mpi.assign(md, md + ml);
-  else if (read_mpi(b, n, p, md, ml, bits)) return kStructural;   // DSA/ECDSA: r and s must be well formed
+  else {                                                           // DSA/ECDSA: r and s must be well formed
+    while (ml && *md == 0) { md++; ml--; }
+    s.r.assign(md, md + ml);
+    if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
+    while (ml && *md == 0) { md++; ml--; }
+    s.s.assign(md, md + ml);
+  }
   return kOk;
 }
 
@@ -192,7 +199,13 @@ struct PubKey {
   uint32_t e = 0;
   unsigned nbits = 0;
   int32_t table_idx = -1;        // index in the engine's key table, -1: not verifiable on the device
+  std::vector<uint8_t> ec_xy;    // ECDSA on P-256: X || Y (64 bytes); empty for other curves
+  std::vector<uint8_t> dsa[4];   // DSA: p, q, g, y (stripped big-endian)
 };
+inline void strip_assign(std::vector<uint8_t>& out, const uint8_t* md, size_t ml) {
+  while (ml && *md == 0) { md++; ml--; }
+  out.assign(md, md + ml);
+}
 
 // SHA-1 only for key ids (fingerprint of the public-key packet) — identification, not verification.
 inline void sha1(const uint8_t* m, size_t len, uint8_t out[20]) {
@@ -234,7 +247,25 @@ inline int parse_public_key(const uint8_t* b, size_t n, PubKey& k) {
     if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
     if (ml > 3) return kUnsupported;          // "large public exponent"
     k.e = 0; for (size_t i = 0; i < ml; i++) k.e = (k.e << 8) | md[i];
-  } else if (k.algo != 16 && k.algo != 17 && k.algo != 18 && k.algo != 19) {
+  } else if (k.algo == 19) {                     // parseECDSA: OID then the uncompressed point as one MPI
+    if (n < 7) return kStructural;
+    const size_t ol = b[6];
+    if (ol == 0 || ol == 0xff || 7 + ol > n) return kStructural;
+    static const uint8_t p256_oid[8] = {0x2A, 0x86, 0x48, 0xCE, 0x3D, 0x03, 0x01, 0x07};
+    const bool p256 = ol == 8 && memcmp(b + 7, p256_oid, 8) == 0;
+    size_t p = 7 + ol; const uint8_t* md; size_t ml; unsigned bits;
+    if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
+    if (p256 && ml == 65 && md[0] == 4) k.ec_xy.assign(md + 1, md + 65);
+    k.nbits = 256;
+  } else if (k.algo == 17) {                     // parseDSA: p, q, g, y
+    size_t p = 6; const uint8_t* md; size_t ml; unsigned bits;
+    for (int i = 0; i < 4; i++) {
+      if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
+      strip_assign(k.dsa[i], md, ml);
+    }
+    const auto& P = k.dsa[0];
+    k.nbits = P.empty() ? 0 : (unsigned)(8 * (P.size() - 1) + (32 - __builtin_clz((unsigned)P[0])));
+  } else if (k.algo != 16 && k.algo != 18) {
     return kUnsupported;
   }
   std::vector<uint8_t> fp(3 + n);

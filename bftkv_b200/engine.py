@@ -157,6 +157,35 @@ class Engine:
         _lib.check(self._lib.bftq_ed25519_verify_batch(self._h, _ptr(pubkeys), pubkeys.shape[0], _ptr(key_idx), _ptr(sig), _ptr(msg), n, _ptr(out)))
         return out
 
+    # ---- K1c ----
+    def ecdsa_p256_verify_batch(self, pubkeys, key_idx, r_be, s_be, digest):
+        """pubkeys (K,64) X||Y, key_idx (N,) uint32, r_be/s_be (N,32), digest (N,dlen) uint8 -> status (N,)."""
+        pubkeys = np.ascontiguousarray(pubkeys, np.uint8)
+        key_idx = np.ascontiguousarray(key_idx, np.uint32)
+        r_be = np.ascontiguousarray(r_be, np.uint8)
+        s_be = np.ascontiguousarray(s_be, np.uint8)
+        digest = np.ascontiguousarray(digest, np.uint8)
+        n = int(key_idx.shape[0])
+        out = np.empty(n, np.uint8)
+        _lib.check(self._lib.bftq_ecdsa_p256_verify_batch(self._h, _ptr(pubkeys), pubkeys.shape[0], _ptr(key_idx), _ptr(r_be),
+                                                          _ptr(s_be), _ptr(digest), digest.shape[1] if n else 32, n, _ptr(out)))
+        return out
+
+    # ---- K1d ----
+    def dsa_verify_batch(self, p: int, q: int, g: int, y: int, r_be, s_be, digest):
+        """One DSA key (p, q, g, y); r_be/s_be (N,32), digest (N,dlen) uint8 -> status (N,)."""
+        plen, qlen = (p.bit_length() + 7) // 8, (q.bit_length() + 7) // 8
+        pb, qb = self._be([p], plen), self._be([q], qlen)
+        gb, yb = self._be([g % p], plen), self._be([y % p], plen)
+        r_be = np.ascontiguousarray(r_be, np.uint8)
+        s_be = np.ascontiguousarray(s_be, np.uint8)
+        digest = np.ascontiguousarray(digest, np.uint8)
+        n = int(r_be.shape[0])
+        out = np.empty(n, np.uint8)
+        _lib.check(self._lib.bftq_dsa_verify_batch(self._h, _ptr(pb), plen, _ptr(qb), qlen, _ptr(gb), _ptr(yb), _ptr(r_be), _ptr(s_be),
+                                                   _ptr(digest), digest.shape[1] if n else 32, n, _ptr(out)))
+        return out
+
     # ---- K5 ----
     @staticmethod
     def _be(vals, width):

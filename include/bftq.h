@@ -139,6 +139,28 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* d_pubkeys, uint
                                   const uint8_t* d_sig, const uint8_t* d_msg, uint64_t n_items, uint8_t* d_status,
                                   void* cuda_stream);
 
+/* ---- K1c: batched ECDSA P-256 verify -----------------------------------------------------------
+ * Replaces the PubKeyAlgoECDSA arm of packet.PublicKey.VerifySignature (x/crypto openpgp/packet/
+ * public_key.go, reached from crypto/pgp/pgp.go:593 via CheckDetachedSignature) = Go crypto/ecdsa.Verify:
+ * 0 < r, s < N, e = leftmost min(len, 32) digest bytes, (x, y) = (e/s) G + (r/s) Q, valid iff finite and
+ * x mod N == r (no low-s rule).  pubkeys: n_keys x 64 (X || Y), r_be / s_be: n_items x 32 (MPIs left-
+ * padded), digest: n_items x digest_len (<= 64).  out_status: BFTQ_ST_OK / _BAD_SIGNATURE / _MALFORMED
+ * (key not on the curve) / _UNKNOWN_SIGNER (key index out of range). */
+int bftq_ecdsa_p256_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* key_idx,
+                                 const uint8_t* r_be, const uint8_t* s_be, const uint8_t* digest, uint32_t digest_len,
+                                 uint64_t n_items, uint8_t* out_status);
+
+/* ---- K1d: batched DSA verify (one key per call) -------------------------------------------------
+ * Replaces the PubKeyAlgoDSA arm of packet.PublicKey.VerifySignature (digest cut to the subgroup size) =
+ * Go crypto/dsa.Verify: 0 < r, s < q, w = s^-1 mod q, v = (g^(z w) y^(r w) mod p) mod q, valid iff v == r;
+ * false for every signature when q's bit length is not a multiple of 8.  p_be/g_be/y_be: plen bytes
+ * (plen 128 or 256, p odd with exactly 8*plen bits), q_be: qlen <= 32 bytes, q an odd PRIME (the inverse is
+ * taken by Fermat).  r_be / s_be: n_items x 32 (MPIs left-padded), digest: n_items x digest_len (<= 64).
+ * out_status: BFTQ_ST_OK / _BAD_SIGNATURE.  Other domain sizes: BFTQ_ERR_UNSUPPORTED_KEY. */
+int bftq_dsa_verify_batch(bftq_engine* e, const uint8_t* p_be, uint32_t plen, const uint8_t* q_be, uint32_t qlen, const uint8_t* g_be,
+                          const uint8_t* y_be, const uint8_t* r_be, const uint8_t* s_be, const uint8_t* digest, uint32_t digest_len,
+                          uint64_t n_items, uint8_t* out_status);
+
 /* ---- K2: batched wotqs quorum tally ---------------------------------------------------------
  * A quorum descriptor is what wotqs.getQuorumFrom builds (quorum/wotqs/wotqs.go:95-115): a list of
  * quorum cliques qc{nodes,f,min,threshold,suff} (wotqs.go:16-22, values from newQC :36-70).

@@ -153,6 +153,9 @@ class PublicKey:
     fingerprint: bytes = b""
     is_subkey: bool = False
     body: bytes = b""
+    ec_oid: bytes = b""
+    ec_point: Optional[Tuple[int, int]] = None      # P-256 only
+    dsa: Optional[Tuple[int, int, int, int]] = None  # p, q, g, y
 
 
 def parse_public_key(body: bytes, is_subkey: bool = False) -> PublicKey:
@@ -165,8 +168,26 @@ def parse_public_key(body: bytes, is_subkey: bool = False) -> PublicKey:
         pk.e, ebits, p = read_mpi(body, p)
         if (ebits + 7) // 8 > 3:
             raise UnsupportedError("large public exponent")
-    elif algo in (16, 17, 18, 19):
-        pass      # ElGamal / DSA / ECDH / ECDSA: parsed by x/crypto, not verifiable on this path yet
+    elif algo == 19:
+        # x/crypto packet/public_key.go parseECDSA + newECDSA: one length octet, the curve OID, then the
+        # SEC1 uncompressed point as one MPI; elliptic.Unmarshal needs 04 || X || Y on the curve.
+        ol = body[6] if len(body) > 6 else 0
+        if ol in (0, 0xff) or 7 + ol > len(body):
+            raise StructuralError("invalid oid length")
+        pk.ec_oid = body[7:7 + ol]
+        pt, bits, p = read_mpi(body, 7 + ol)
+        raw = body[7 + ol + 2:p]
+        if pk.ec_oid == bytes([0x2A, 0x86, 0x48, 0xCE, 0x3D, 0x03, 0x01, 0x07]) and len(raw) == 65 and raw[0] == 4:
+            pk.ec_point = (int.from_bytes(raw[1:33], "big"), int.from_bytes(raw[33:], "big"))
+    elif algo == 17:
+        # parseDSA: p, q, g, y
+        vals, p = [], 6
+        for _ in range(4):
+            v, bits, p = read_mpi(body, p)
+            vals.append(v)
+        pk.dsa = tuple(vals)
+    elif algo in (16, 18):
+        pass      # ElGamal / ECDH: parsed by x/crypto, never signature keys
     else:
         raise UnsupportedError("public key type: %d" % algo)
     fp = hashlib.sha1(b"\x99" + len(body).to_bytes(2, "big") + body).digest()
@@ -192,6 +213,8 @@ class Signature:
     flag_sign: bool = False
     is_primary_id: Optional[bool] = None
     revocation_reason: Optional[int] = None
+    sig_r: int = 0                    # DSA / ECDSA
+    sig_s: int = 0
     rsa_sig: int = 0
     rsa_sig_bytes: bytes = b""        # MPI bytes as stored (leading zeros stripped)
     raw: bytes = b""
@@ -293,7 +316,8 @@ def parse_signature(body: bytes) -> Signature:
         sig.rsa_sig, bits, q = read_mpi(body, p)
         sig.rsa_sig_bytes = body[p + 2:q]
     else:
-        read_mpi(body, read_mpi(body, p)[2])      # r, s must at least be well-formed
+        sig.sig_r, bits, q = read_mpi(body, p)      # DSASigR / ECDSASigR
+        sig.sig_s, bits, q = read_mpi(body, q)
     return sig
 
 
@@ -467,6 +491,44 @@ def rsa_verify_pkcs1v15(n: int, e: int, hash_id: int, digest: bytes, sig_bytes: 
     return em == b"\x00\x01" + b"\xff" * (k - tlen - 3) + b"\x00" + prefix + digest
 
 
+def ecdsa_p256_verify(q: Tuple[int, int], digest: bytes, r: int, s: int) -> bool:
+    """Go crypto/ecdsa.Verify on P-256 (ecdsa.go Verify + hashToInt): no low-s rule; the digest is cut
+    to its leftmost 32 bytes."""
+    from . import sss_oracle as so
+    n = so.P256_N
+    if r <= 0 or s <= 0 or r >= n or s >= n:
+        return False
+    x, y = q
+    if (y * y - (x * x * x - 3 * x + so.P256_B)) % so.P256_P != 0 or x >= so.P256_P or y >= so.P256_P:
+        return False                                # elliptic.Unmarshal would have refused the key
+    e = int.from_bytes(digest[:32], "big")
+    w = pow(s, -1, n)
+    pt = so.p256_add(so.p256_mul(e * w % n, so.P256_G), so.p256_mul(r * w % n, q))
+    if pt is None:
+        return False
+    return pt[0] % n == r
+
+
+def dsa_verify(p: int, q: int, g: int, y: int, digest: bytes, r: int, s: int) -> bool:
+    """x/crypto VerifySignature's DSA arm (digest cut to the subgroup size) + Go crypto/dsa.Verify."""
+    sub = (q.bit_length() + 7) // 8
+    digest = digest[:sub]
+    if p == 0:
+        return False
+    if r < 1 or r >= q or s < 1 or s >= q:
+        return False
+    try:
+        w = pow(s, -1, q)
+    except ValueError:
+        return False
+    if q.bit_length() & 7:
+        return False
+    z = int.from_bytes(digest, "big")
+    u1, u2 = z * w % q, r * w % q
+    v = pow(g, u1, p) * pow(y, u2, p) % p % q
+    return v == r
+
+
 def verify_signature(pk: PublicKey, signed: bytes, sig: Signature):
     """packet.PublicKey.VerifySignature.  Raises SignatureError / UnsupportedError."""
     digest = signature_digest(signed, sig)
@@ -477,6 +539,14 @@ def verify_signature(pk: PublicKey, signed: bytes, sig: Signature):
     if pk.algo in (1, 3):
         if not rsa_verify_pkcs1v15(pk.n, pk.e, sig.hash_id, digest, sig.rsa_sig_bytes):
             raise SignatureError("RSA verification failure")
+        return
+    if pk.algo == 19 and pk.ec_point is not None:
+        if not ecdsa_p256_verify(pk.ec_point, digest, sig.sig_r, sig.sig_s):
+            raise SignatureError("ECDSA verification failure")
+        return
+    if pk.algo == 17 and pk.dsa is not None:
+        if not dsa_verify(*pk.dsa, digest, sig.sig_r, sig.sig_s):
+            raise SignatureError("DSA verification failure")
         return
     raise UnsupportedError("oracle: public key algorithm %d not restated" % pk.algo)
 

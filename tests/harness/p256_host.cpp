@@ -15,4 +15,9 @@ int p256_add_host(const uint8_t* a, const uint8_t* b, uint8_t* out65) {
   pt r; pt_add(r, p, q); out65[0] = 4;
   return pt_to_affine(out65 + 1, out65 + 33, r) ? 1 : 2;
 }
+int p256_ecdsa_verify_host(const uint8_t* pub65, const uint8_t* r_be, const uint8_t* s_be, const uint8_t* digest, int dlen) {
+  pt q; if (!pt_from_uncompressed(q, pub65)) return -1;
+  uint32_t r[8], s[8]; be_to_limbs(r, r_be); be_to_limbs(s, s_be);
+  return ecdsa_verify_core(q, r, s, digest, dlen) ? 1 : 0;
+}
 }
