@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MACS_PER_VERIFY = 156864          # 19 Montgomery products x (2*64^2 + 64) word-MACs, SURVEY §8(d)
+NCU_DRAM_BYTES_PER_LAUNCH = 19272448      # profiles/ncu_rsa_verify_r01c_r32.txt: 19.272448 MB read + 0 B written per 65536-item launch
 BYTES_PER_VERIFY = 549            # n 256 + s 256 + digest 32 + key idx 4 + status 1, SURVEY §8(d)
 ITEMS = 65536
 NKEYS = 16
@@ -344,7 +345,9 @@ def run_gpu(args, rank, local_rank, world):
                                   "data": "synthetic; 1,048,576 tuples drawn from a pool of 65,536 genuine signatures"},
                        "kernels_per_step": 2},
         "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE on the FMA-heavy pipe)",
-                     "frac": achieved / int_peak, "traffic": None,
+                     "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rsa_verify_r32_kernel launch (65536 items) in "
+                                       "profiles/ncu_rsa_verify_r01c_r32.txt (ncu --set full); algorithmic bytes per launch = %d" % (BYTES_PER_VERIFY * ITEMS),
                      "peak_source": "measured live on this GPU: dependency-free fused IMAD.WIDE.U32 stream, 64 warps/SM (bftq_measure_int_peak)",
                      "kernel": "rsa_verify_kernel", "kernel_ms_avg": k_avg_ms, "kernel_ms_min": kernel_ms[0],
                      "algorithmic_macs_per_verify": MACS_PER_VERIFY,
