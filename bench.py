@@ -150,10 +150,15 @@ def run_gpu(args, rank, local_rank, world):
     d_dig = [torch.from_numpy(w["digest"]).to(dev) for _ in range(copies)]
     d_st = [torch.empty(ITEMS, dtype=torch.uint8, device=dev) for _ in range(copies)]
     stream = torch.cuda.Stream(device=dev)
+    # The timed launches alternate over NSTREAMS streams: the blocks of batch i+1 fill the partially occupied last
+    # wave of batch i and the two batches run out of phase (one loads / compares while the other multiplies) —
+    # what a server with several batches in flight gets anyway (tools/tail_experiment.py: +7.6 % over one stream).
+    NSTREAMS = max(1, args.streams)
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS - 1)]
 
-    def step(i):
+    def step(i, st=None):
         c = i % copies
-        eng.rsa_verify_batch_dev(d_idx[c], d_sig[c], d_dig[c], ITEMS, d_st[c], stream=stream.cuda_stream)
+        eng.rsa_verify_batch_dev(d_idx[c], d_sig[c], d_dig[c], ITEMS, d_st[c], stream=(st or stream).cuda_stream)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -161,23 +166,35 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # warm-up, serial on one stream, with per-launch events: the duration of one launch running alone
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.warmup + 1)]
+    evs[0].record(stream)
     for i in range(args.warmup):
         step(i)
+        evs[i + 1].record(stream)
+    stream.synchronize()
+    serial_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(1, args.warmup)) or [evs[0].elapsed_time(evs[1])]
+    for i in range(NSTREAMS):
+        step(i, streams[i])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.stats()["launches"]
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    evs[0].record(stream)
+    ev0.record(stream)
+    for st in streams[1:]:
+        st.wait_event(ev0)
     for i in range(args.steps):
-        step(i)
-        evs[i + 1].record(stream)
+        step(i, streams[i % NSTREAMS])
+    for st in streams[1:]:
+        stream.wait_stream(st)
+    ev1.record(stream)
     stream.synchronize()
     barrier()
-    dev_ms = evs[0].elapsed_time(evs[-1])
-    kernel_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    dev_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [dev_ms / args.steps]
     gpu_launches = eng.stats()["launches"] - launches0
     for c in range(min(copies, args.steps)):
         assert np.array_equal(d_st[c].cpu().numpy(), w["expect"]), "device-resident results differ from expectation"
@@ -333,7 +350,7 @@ def run_gpu(args, rank, local_rank, world):
         "config": {"workload": "batch 65536 RSA-2048 PGP signature verifies (BASELINE configs[1]), 16 keys, e=65537, SHA-256, "
                                "1% corrupted + 0.1% unknown signer",
                    "per_gpu_batch": ITEMS, "l2": "inputs rotated over %d distinct device copies (%d MB > 126 MB L2)"
-                   % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4"))},
+                   % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4")), "streams_in_flight": NSTREAMS},
         "gpu_launches": int(gpu_launches),
         "e2e": {"value": e2e_v, "unit": "verifies/s", "h2d_bytes_per_step": ITEMS * (256 + 32 + 4), "d2h_bytes_per_step": ITEMS,
                 "api": "bftq_rsa_verify_batch (host C ABI, pinned host buffers), %d concurrent callers" % NCALLERS,
@@ -349,7 +366,8 @@ def run_gpu(args, rank, local_rank, world):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rsa_verify_r32_kernel launch (65536 items) in "
                                        "profiles/ncu_rsa_verify_r01c_r32.txt (ncu --set full); algorithmic bytes per launch = %d" % (BYTES_PER_VERIFY * ITEMS),
                      "peak_source": "measured live on this GPU: dependency-free fused IMAD.WIDE.U32 stream, 64 warps/SM (bftq_measure_int_peak)",
-                     "kernel": "rsa_verify_kernel", "kernel_ms_avg": k_avg_ms, "kernel_ms_min": kernel_ms[0],
+                     "kernel": "rsa_verify_r32_kernel", "kernel_ms_avg": k_avg_ms, "kernel_ms_alone": serial_ms[len(serial_ms) // 2],
+                     "kernel_ms_note": "avg = timed region / launches (launches alternate over %d streams); alone = median of the serial warm-up launches" % NSTREAMS,
                      "algorithmic_macs_per_verify": MACS_PER_VERIFY,
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "peak_source": hbm_src + " (MEASURED_PEAKS.json)", "algorithmic_bytes_per_verify": BYTES_PER_VERIFY}},
@@ -376,7 +394,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--copies", type=int, default=8)
-    ap.add_argument("--callers", type=int, default=2, help="concurrent host callers in the end-to-end leg")
+    ap.add_argument("--streams", type=int, default=2, help="streams the device-resident launches alternate over")
+    ap.add_argument("--callers", type=int, default=4, help="concurrent host callers in the end-to-end leg")
     ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
