@@ -55,6 +55,7 @@ def load():
         "bftq_ed25519_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),
         "bftq_ed25519_verify_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp, vp]),
         "bftq_modprod_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]),
+        "bftq_signature_plan_measure": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
         "bftq_signature_parse": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, vp, C.c_uint32, u32p, C.POINTER(C.c_int32)]),
         "bftq_ecdsa_p256_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint32, C.c_uint64, vp]),
         "bftq_dsa_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint64, vp]),

@@ -15,6 +15,7 @@
 #include "wotqs_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,6 +96,7 @@ struct StagingSlot {
   cudaStream_t stream = nullptr;
   uint8_t* h_pinned = nullptr;  size_t h_cap = 0;
   uint8_t* d_buf = nullptr;     size_t d_cap = 0;
+  cudaEvent_t done = nullptr;   // blocking-sync event: a waiting packer thread sleeps instead of spinning
   bool busy = false;
 };
 
@@ -117,33 +119,48 @@ struct bftq_engine {
   struct DsaKey { std::vector<uint8_t> p, q, gy; int cls; };   // gy: g || y, each padded to |p| bytes
   std::vector<DsaKey> dsa_keys;                  // host table; a group's domain travels with its launch
   std::map<std::string, uint32_t> dsa_lookup;
+  std::atomic<int> packer_workers{0};            // packer worker threads alive across all concurrent batch calls
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
 
 namespace {
 
+// Picks a free staging slot: the smallest one that is already large enough, else the largest free one
+// (which then grows), else a new one.  Growing means cudaFreeHost / cudaHostAlloc / cudaMalloc — calls that
+// stall the whole device — so capacities are rounded up to a power of two (at least 1 MiB): calls of varying
+// size settle on a stable pool after a few batches instead of reallocating for ever.
 int acquire_slot(bftq_engine* e, size_t h_bytes, size_t d_bytes, StagingSlot** out) {
   StagingSlot* s = nullptr;
   {
     std::lock_guard<std::mutex> g(e->mu);
-    for (auto* c : e->slots) if (!c->busy) { s = c; break; }
+    StagingSlot *fit = nullptr, *big = nullptr;
+    for (auto* c : e->slots) {
+      if (c->busy) continue;
+      if (c->h_cap >= h_bytes && c->d_cap >= d_bytes) { if (!fit || c->h_cap < fit->h_cap) fit = c; }
+      else if (!big || c->h_cap > big->h_cap) big = c;
+    }
+    s = fit ? fit : big;
     if (!s) { s = new StagingSlot(); e->slots.push_back(s); }
     s->busy = true;
   }
+  auto round_up = [](size_t v) { size_t c = (size_t)1 << 20; while (c < v) c <<= 1; return c; };
   CU(cudaSetDevice(e->device));
   if (!s->stream) CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (!s->done) CU(cudaEventCreateWithFlags(&s->done, cudaEventBlockingSync | cudaEventDisableTiming));
   if (s->h_cap < h_bytes) {
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     s->h_pinned = nullptr; s->h_cap = 0;
-    CU(cudaHostAlloc((void**)&s->h_pinned, h_bytes, cudaHostAllocDefault));
-    s->h_cap = h_bytes;
+    const size_t cap = round_up(h_bytes);
+    CU(cudaHostAlloc((void**)&s->h_pinned, cap, cudaHostAllocDefault));
+    s->h_cap = cap;
   }
   if (s->d_cap < d_bytes) {
     if (s->d_buf) cudaFree(s->d_buf);
     s->d_buf = nullptr; s->d_cap = 0;
-    CU(cudaMalloc((void**)&s->d_buf, d_bytes));
-    s->d_cap = d_bytes;
+    const size_t cap = round_up(d_bytes);
+    CU(cudaMalloc((void**)&s->d_buf, cap));
+    s->d_cap = cap;
   }
   *out = s;
   return BFTQ_OK;
@@ -163,19 +180,52 @@ class Arena {
   template <typename T> void out(T** dptr, T* host, size_t count, size_t copy = (size_t)-1) {
     add((void**)dptr, (void*)host, count * sizeof(T), (copy == (size_t)-1 ? count : copy) * sizeof(T), false);
   }
+  // An input the caller composes in place: after prepare(), *hptr is the slot's pinned mirror of the
+  // buffer (write `count` elements there), so the bytes cross host memory once.
+  template <typename T> void stage(T** dptr, T** hptr, size_t count) {
+    add((void**)dptr, nullptr, count * sizeof(T), count * sizeof(T), true);
+    bufs_.back().hptr = (void**)hptr;
+  }
   cudaStream_t stream() const { return s_->stream; }
-  int upload() {
+  // Acquires the staging slot and resolves every device (and staged host) pointer.  upload() calls it
+  // when the caller has not.
+  int prepare() {
+    if (s_) return BFTQ_OK;
     int rc = acquire_slot(e_, total_, total_, &s_);
     if (rc) return rc;
-    uint64_t h2d = 0;
     for (auto& b : bufs_) {
       *b.dptr = s_->d_buf + b.off;
-      if (!b.is_in || b.copy == 0) continue;
-      const void* from = b.host;
-      if (!is_pinned(b.host)) { memcpy(s_->h_pinned + b.off, b.host, b.copy); from = s_->h_pinned + b.off; }
-      CU(cudaMemcpyAsync(s_->d_buf + b.off, from, b.copy, cudaMemcpyHostToDevice, s_->stream));
-      h2d += b.copy;
+      if (b.hptr) { *b.hptr = s_->h_pinned + b.off; b.host = s_->h_pinned + b.off; }
     }
+    return BFTQ_OK;
+  }
+  int upload() {
+    int rc = prepare();
+    if (rc) return rc;
+    uint64_t h2d = 0;
+    // Inputs that live in the slot's pinned mirror (staged in place or bounced) have the same layout on
+    // both sides, so neighbours travel in ONE copy: a chunk of the packer costs one H2D call, not nine
+    // (driver calls from many worker threads serialise on the context lock).
+    size_t run_lo = (size_t)-1, run_hi = 0;
+    auto flush = [&]() -> cudaError_t {
+      if (run_lo == (size_t)-1) return cudaSuccess;
+      cudaError_t ce = cudaMemcpyAsync(s_->d_buf + run_lo, s_->h_pinned + run_lo, run_hi - run_lo, cudaMemcpyHostToDevice, s_->stream);
+      run_lo = (size_t)-1;
+      return ce;
+    };
+    for (auto& b : bufs_) {
+      if (!b.is_in || b.copy == 0) continue;
+      h2d += b.copy;
+      if (!b.hptr && is_pinned(b.host)) {                      // caller's pinned memory: DMA straight from it
+        CU(cudaMemcpyAsync(s_->d_buf + b.off, b.host, b.copy, cudaMemcpyHostToDevice, s_->stream));
+        continue;
+      }
+      if (!b.hptr) memcpy(s_->h_pinned + b.off, b.host, b.copy);
+      if (run_lo != (size_t)-1 && b.off - run_hi > 65536) CU(flush());      // do not drag a large output region along
+      if (run_lo == (size_t)-1) run_lo = b.off;
+      run_hi = b.off + b.copy;
+    }
+    CU(flush());
     std::lock_guard<std::mutex> g(e_->mu);
     e_->stats.h2d_bytes += h2d;
     return BFTQ_OK;
@@ -199,21 +249,26 @@ class Arena {
       }
       d2h += b.copy;
     }
+    if (sleepy_) { CU(cudaEventRecord(s_->done, s_->stream)); recorded_ = true; }
     std::lock_guard<std::mutex> g(e_->mu);
     e_->stats.d2h_bytes += d2h;
     return BFTQ_OK;
   }
+  // sleepy = wait on a blocking-sync event (the thread sleeps until the copy has landed) instead of spinning
+  // in cudaStreamSynchronize: the packer's workers share the host's CPU quota with the threads still parsing.
+  void set_sleepy(bool v) { sleepy_ = v; }
   int finish() {
-    CU(cudaStreamSynchronize(s_->stream));
+    if (sleepy_ && recorded_) CU(cudaEventSynchronize(s_->done));
+    else CU(cudaStreamSynchronize(s_->stream));
     for (auto* b : bounce_) memcpy(b->host, s_->h_pinned + b->off, b->copy);
     bounce_.clear();
     return BFTQ_OK;
   }
 
  private:
-  struct Buf { void** dptr; void* host; size_t off, bytes, copy; bool is_in; };
+  struct Buf { void** dptr; void* host; size_t off, bytes, copy; bool is_in; void** hptr; };
   void add(void** dptr, void* host, size_t bytes, size_t copy, bool is_in) {
-    bufs_.push_back({dptr, host, total_, bytes, copy, is_in});
+    bufs_.push_back({dptr, host, total_, bytes, copy, is_in, nullptr});
     total_ += (bytes + 255) & ~(size_t)255;
   }
   static bool is_pinned(const void* p) {
@@ -224,6 +279,7 @@ class Arena {
   }
   bftq_engine* e_;
   StagingSlot* s_ = nullptr;
+  bool sleepy_ = false, recorded_ = false;
   std::vector<Buf> bufs_;
   std::vector<const Buf*> bounce_;
   size_t total_ = 0;
@@ -348,6 +404,7 @@ void bftq_shutdown(bftq_engine* e) {
   cudaSetDevice(e->device);
   for (auto* s : e->slots) {
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    if (s->done) cudaEventDestroy(s->done);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->d_buf) cudaFree(s->d_buf);
     delete s;
@@ -1206,25 +1263,34 @@ void index_entity_keys(bftq_engine* e, pg::Entity& ent) {
 }
 
 struct Tuple {
-  uint32_t item, call;
+  uint32_t item, call;         // item = index inside the plan (chunk-local)
   int32_t key_idx;
+  uint32_t kbytes;             // RSA: key-size class of the candidate key (signature is padded to it); DSA: key table index
   uint64_t signer_id;          // primary key id of the candidate key's entity
+  uint32_t data_idx;
+  uint32_t suffix_pos, suffix_len;   // into Plan::suffix_blob
+  uint32_t sig_pos;            // into Plan::sig_blob, sig_bytes_of(alg, kbytes) bytes
+  uint16_t tag;
   uint8_t pre;                 // status decided on the host (0 = ask the GPU)
   uint8_t hash_id;
   uint8_t alg;                 // 1: RSA (K1), 19: ECDSA P-256 (K1c), 17: DSA (K1d)
-  uint32_t kbytes;             // RSA: key-size class of the candidate key (signature is padded to it); DSA: key table index
-  uint16_t tag;
-  uint32_t data_idx;
-  uint32_t suffix_pos, suffix_len;   // into suffix blob
-  uint8_t sig[512];            // RSA: signature padded to kbytes.  ECDSA: r (32) || s (32) || X (32) || Y (32).  DSA: r (32) || s (32)
 };
+// Bytes a tuple occupies in the signature blob.  RSA: the signature padded to the key size.
+// ECDSA: r (32) || s (32) || X (32) || Y (32).  DSA: r (32) || s (32).
+inline uint32_t sig_bytes_of(uint8_t alg, uint32_t kbytes) { return alg == 19 ? 128u : (alg == 17 ? 64u : kbytes); }
+
 struct Plan {
   std::vector<Tuple> tuples;
   std::vector<uint32_t> calls_per_item;     // number of CheckDetachedSignature calls that reached a known issuer
   std::vector<uint8_t> item_failed;          // Verify mode: a structural error / unknown issuer ended the stream
   std::vector<uint8_t> suffix_blob;
+  std::vector<uint8_t> sig_blob;
   std::vector<uint8_t> data_blob;            // tbs strings, plus CRLF-canonicalised copies when needed
   std::vector<uint64_t> data_off;
+  void reset() {
+    tuples.clear(); calls_per_item.clear(); item_failed.clear(); suffix_blob.clear(); sig_blob.clear(); data_blob.clear();
+    data_off.clear(); data_off.push_back(0);
+  }
 };
 
 void canonical_text(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
@@ -1239,21 +1305,22 @@ void canonical_text(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
 // tolerant loop (crypto_pgp.go:485-500), else Signature.Verify's strict one (:319-330).
 void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, const uint8_t* sig, size_t sig_len,
                const std::vector<const std::vector<pg::Entity>*>& rings, bool collective) {
+  static thread_local std::vector<uint8_t> scratch;
+  static thread_local std::vector<pg::KeyRef> keys;
   const uint32_t data_plain = (uint32_t)pl.data_off.size() - 1;
   pl.data_blob.insert(pl.data_blob.end(), tbs, tbs + tbs_len);
   pl.data_off.push_back(pl.data_blob.size());
   int32_t data_text = -1;
   pg::Reader r{sig, sig_len, 0};
-  std::vector<uint8_t> scratch;
-  std::vector<pg::KeyRef> keys;
   pg::SigPacket sp;
   uint32_t calls = 0;
   bool failed = false;
   while (r.remaining() > 0) {
     const int rc = pg::next_known_signature(r, rings, sp, keys, scratch);
     if (rc == pg::kOk) {
-      const uint32_t spos = (uint32_t)pl.suffix_blob.size();
-      pl.suffix_blob.insert(pl.suffix_blob.end(), sp.suffix.begin(), sp.suffix.end());
+      const uint32_t spos = (uint32_t)pl.suffix_blob.size(), slen = (uint32_t)sp.suffix_size();
+      pl.suffix_blob.resize((size_t)spos + slen);
+      sp.write_suffix(pl.suffix_blob.data() + spos);
       uint32_t didx = data_plain;
       uint8_t common_pre = 0;
       if (sp.version != 4) common_pre = BFTQ_ST_UNSUPPORTED;                    // SignatureV3: not built
@@ -1271,42 +1338,38 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
       if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // MD5 / RIPEMD-160: not built
       for (const pg::KeyRef& kr : keys) {
         Tuple t;
-        memset(&t, 0, sizeof(t));
         t.item = item; t.call = calls; t.signer_id = kr.entity->primary.key_id;
         t.tag = (uint16_t)((sp.hash_tag[0] << 8) | sp.hash_tag[1]);
-        t.data_idx = didx; t.suffix_pos = spos; t.suffix_len = (uint32_t)sp.suffix.size();
+        t.data_idx = didx; t.suffix_pos = spos; t.suffix_len = slen;
         t.pre = common_pre;
         t.hash_id = sp.hash_id;
         t.key_idx = kr.key->table_idx;
         if (!t.pre && kr.key->algo != sp.pk_algo) t.pre = BFTQ_ST_BAD_SIGNATURE;   // "different algorithms"
         if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
         if (t.key_idx < 0) t.key_idx = 0;
-        t.alg = 1;
-        if (sp.pk_algo == 19 && kr.key->algo == 19) {                               // ecdsa.Verify: r, s >= N (any longer than 32 bytes) fail
-          t.alg = 19; t.kbytes = 0;
+        t.alg = 1; t.kbytes = 0;
+        const bool ec = sp.pk_algo == 19 && kr.key->algo == 19, dsa = sp.pk_algo == 17 && kr.key->algo == 17;
+        if (ec) t.alg = 19;
+        else if (dsa) { t.alg = 17; t.kbytes = (uint32_t)t.key_idx; }
+        else {
+          const size_t kb = (kr.key->nbits + 7) / 8;                                  // pub.Size()
+          t.kbytes = (uint32_t)(bftq::class_supported((int)kb) ? kb : 256);
+        }
+        const uint32_t nb = sig_bytes_of(t.alg, t.kbytes);
+        t.sig_pos = (uint32_t)pl.sig_blob.size();
+        pl.sig_blob.resize((size_t)t.sig_pos + nb);                                   // zero-filled
+        uint8_t* dst = pl.sig_blob.data() + t.sig_pos;
+        if (ec || dsa) {           // ecdsa.Verify / dsa.Verify: r, s >= N resp. q (any longer than 32 bytes) fail
           if (sp.r.size() > 32 || sp.s.size() > 32) { if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE; }
           else {
-            memcpy(t.sig + 32 - sp.r.size(), sp.r.data(), sp.r.size());
-            memcpy(t.sig + 64 - sp.s.size(), sp.s.data(), sp.s.size());
+            if (sp.r.size()) memcpy(dst + 32 - sp.r.size(), sp.r.data(), sp.r.size());
+            if (sp.s.size()) memcpy(dst + 64 - sp.s.size(), sp.s.data(), sp.s.size());
           }
-          if (kr.key->ec_xy.size() == 64) memcpy(t.sig + 64, kr.key->ec_xy.data(), 64);
-          pl.tuples.push_back(t);
-          continue;
+          if (ec && kr.key->ec_xy.size() == 64) memcpy(dst + 64, kr.key->ec_xy.data(), 64);
+        } else {
+          if (sp.mpi.size() <= t.kbytes) { if (sp.mpi.size()) memcpy(dst + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size()); }   // padToKeySize
+          else if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE;                             // len(sig) != k
         }
-        if (sp.pk_algo == 17 && kr.key->algo == 17) {                               // dsa.Verify: r, s >= q (q <= 256 bits) fail
-          t.alg = 17; t.kbytes = (uint32_t)t.key_idx;
-          if (sp.r.size() > 32 || sp.s.size() > 32) { if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE; }
-          else {
-            memcpy(t.sig + 32 - sp.r.size(), sp.r.data(), sp.r.size());
-            memcpy(t.sig + 64 - sp.s.size(), sp.s.data(), sp.s.size());
-          }
-          pl.tuples.push_back(t);
-          continue;
-        }
-        const size_t kb = (kr.key->nbits + 7) / 8;                                  // pub.Size()
-        t.kbytes = (uint16_t)(bftq::class_supported((int)kb) ? kb : 256);
-        if (sp.mpi.size() <= t.kbytes) memcpy(t.sig + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size());   // padToKeySize
-        else if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE;                             // len(sig) != k
         pl.tuples.push_back(t);
       }
       calls++;
@@ -1321,67 +1384,103 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
   pl.item_failed.push_back(failed ? 1 : 0);
 }
 
-// digest (K4) -> tag check -> RSA verify (K1) for every tuple of the plan; tuples are grouped by hash
-// algorithm (digest length differs), each group is one K4 + one K1 launch on one stream.
-int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, uint32_t hash_alg, int alg, int kb, std::vector<uint8_t>& status) {
-  const uint32_t dsa_idx = (uint32_t)kb;
-  if (alg == 19) kb = 128;                                   // r || s || X || Y
-  if (alg == 17) kb = 64;                                    // r || s
+// One (hash algorithm, signature algorithm, key-size class) group of a plan in flight on its own
+// stream: digest (K4) -> tag check -> verify (K1 / K1c / K1d).
+struct GroupRun {
+  uint32_t hash_alg = 0; int alg = 0; int kb = 0;
+  std::vector<uint32_t> sel;                 // tuple indices of the group, plan order
+  std::unique_ptr<Arena> arena;              // null: every status was decided on the host
+  std::vector<uint8_t> st;                   // statuses come back here
+};
+
+// Composes the group's flat inputs directly in the staging slot's pinned memory, uploads them and
+// enqueues the kernels and the status download on the slot's stream.  Does not wait.
+int group_enqueue(bftq_engine* e, const Plan& pl, GroupRun& g, std::vector<uint8_t>& status, bool sleepy) {
+  const uint32_t dsa_idx = (uint32_t)g.kb;
+  const uint32_t hash_alg = g.hash_alg;
+  const int alg = g.alg;
+  const int kb = (int)sig_bytes_of((uint8_t)alg, (uint32_t)g.kb);
+  const std::vector<uint32_t>& sel = g.sel;
   const size_t nt = sel.size();
   const int dlen = bftq::host_hash_dlen(hash_alg);
-  std::vector<uint32_t> key_idx(nt), data_idx(nt);
-  std::vector<uint16_t> tags(nt);
-  std::vector<uint8_t> pre(nt), sigs(nt * (size_t)kb), st(nt);
-  std::vector<uint64_t> soff(nt + 1);
-  std::vector<uint8_t> sblob;
-  for (size_t i = 0; i < nt; i++) {
-    const Tuple& t = pl.tuples[sel[i]];
-    key_idx[i] = (uint32_t)t.key_idx; data_idx[i] = t.data_idx; tags[i] = t.tag; pre[i] = t.pre;
-    memcpy(&sigs[i * (size_t)kb], t.sig, kb);
-    soff[i] = sblob.size();
-    sblob.insert(sblob.end(), pl.suffix_blob.begin() + t.suffix_pos, pl.suffix_blob.begin() + t.suffix_pos + t.suffix_len);
-  }
-  soff[nt] = sblob.size();
   if ((alg == 1 && !e->d_keys) || !bftq::digest_on_device(hash_alg)) {   // nothing verifiable: every tuple keeps its host status
-    for (size_t i = 0; i < nt; i++) status[sel[i]] = pre[i] ? pre[i] : (uint8_t)BFTQ_ST_UNSUPPORTED;
+    for (size_t i = 0; i < nt; i++) { const uint8_t pre = pl.tuples[sel[i]].pre; status[sel[i]] = pre ? pre : (uint8_t)BFTQ_ST_UNSUPPORTED; }
     return BFTQ_OK;
   }
-  Arena a(e);
-  uint8_t *d_data, *d_suf, *d_pre, *d_sig, *d_dig, *d_st; uint64_t *d_doff, *d_soff; uint32_t *d_didx, *d_kidx; uint16_t* d_tags;
-  a.in(&d_data, pl.data_blob.data(), std::max<size_t>(pl.data_blob.size(), 1), pl.data_blob.size());
-  a.in(&d_doff, pl.data_off.data(), pl.data_off.size());
-  a.in(&d_suf, sblob.data(), std::max<size_t>(sblob.size(), 1), sblob.size());
-  a.in(&d_soff, soff.data(), soff.size());
-  a.in(&d_didx, data_idx.data(), nt);
-  a.in(&d_kidx, key_idx.data(), nt);
-  a.in(&d_tags, tags.data(), nt);
-  a.in(&d_pre, pre.data(), nt);
-  a.in(&d_sig, sigs.data(), nt * (size_t)kb);
-  a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
   bftq_engine::DsaKey dk;
-  uint8_t *d_gy = nullptr, *d_u = nullptr, *d_pow = nullptr, *d_prod = nullptr;
   if (alg == 17) {
-    { std::lock_guard<std::mutex> g(e->mu); if (dsa_idx < e->dsa_keys.size()) dk = e->dsa_keys[dsa_idx]; }
+    { std::lock_guard<std::mutex> lk(e->mu); if (dsa_idx < e->dsa_keys.size()) dk = e->dsa_keys[dsa_idx]; }
     if (dk.p.empty() || dk.cls != 0) {                     // q's bit length not a multiple of 8: dsa.Verify is false
-      for (size_t i = 0; i < nt; i++) status[sel[i]] = pre[i] ? pre[i] : (uint8_t)(dk.p.empty() ? BFTQ_ST_UNSUPPORTED : BFTQ_ST_BAD_SIGNATURE);
+      for (size_t i = 0; i < nt; i++) {
+        const uint8_t pre = pl.tuples[sel[i]].pre;
+        status[sel[i]] = pre ? pre : (uint8_t)(dk.p.empty() ? BFTQ_ST_UNSUPPORTED : BFTQ_ST_BAD_SIGNATURE);
+      }
       return BFTQ_OK;
     }
+  }
+  size_t suffix_total = 0;
+  for (size_t i = 0; i < nt; i++) suffix_total += pl.tuples[sel[i]].suffix_len;
+  g.arena.reset(new Arena(e));
+  g.st.assign(nt, 0);
+  Arena& a = *g.arena;
+  a.set_sleepy(sleepy);
+  uint8_t *d_data, *d_suf, *d_pre, *d_sig, *d_dig, *d_st; uint64_t *d_doff, *d_soff; uint32_t *d_didx, *d_kidx; uint16_t* d_tags;
+  uint8_t *h_data, *h_suf, *h_pre, *h_sig; uint64_t *h_doff, *h_soff; uint32_t *h_didx, *h_kidx; uint16_t* h_tags;
+  a.stage(&d_data, &h_data, std::max<size_t>(pl.data_blob.size(), 1));
+  a.stage(&d_doff, &h_doff, pl.data_off.size());
+  a.stage(&d_suf, &h_suf, std::max<size_t>(suffix_total, 1));
+  a.stage(&d_soff, &h_soff, nt + 1);
+  a.stage(&d_didx, &h_didx, nt);
+  a.stage(&d_kidx, &h_kidx, nt);
+  a.stage(&d_tags, &h_tags, nt);
+  a.stage(&d_pre, &h_pre, nt);
+  a.stage(&d_sig, &h_sig, nt * (size_t)kb);
+  a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
+  uint8_t *d_gy = nullptr, *d_u = nullptr, *d_pow = nullptr, *d_prod = nullptr;
+  if (alg == 17) {
     a.in(&d_gy, dk.gy.data(), dk.gy.size());
     a.out(&d_u, (uint8_t*)nullptr, 2 * nt * dk.q.size(), 0);
     a.out(&d_pow, (uint8_t*)nullptr, 2 * nt * dk.p.size(), 0);
     a.out(&d_prod, (uint8_t*)nullptr, nt * dk.p.size(), 0);
   }
-  a.out(&d_st, st.data(), nt);
-  int rc = a.upload();
+  a.out(&d_st, g.st.data(), nt);
+  int rc = a.prepare();
+  if (rc) return rc;
+  if (!pl.data_blob.empty()) memcpy(h_data, pl.data_blob.data(), pl.data_blob.size());
+  memcpy(h_doff, pl.data_off.data(), pl.data_off.size() * sizeof(uint64_t));
+  // A group that is the whole plan with one suffix per tuple (the common case: one signature packet per
+  // item, one candidate key) takes the plan's blobs as they are.
+  bool whole = nt == pl.tuples.size() && suffix_total == pl.suffix_blob.size() && nt * (size_t)kb == pl.sig_blob.size();
+  if (whole) {
+    size_t pos = 0;
+    for (size_t i = 0; i < nt && whole; i++) { whole = pl.tuples[i].suffix_pos == pos; pos += pl.tuples[i].suffix_len; }
+  }
+  if (whole) {
+    if (suffix_total) memcpy(h_suf, pl.suffix_blob.data(), suffix_total);
+    if (nt) memcpy(h_sig, pl.sig_blob.data(), nt * (size_t)kb);
+  }
+  size_t spos = 0;
+  for (size_t i = 0; i < nt; i++) {
+    const Tuple& t = pl.tuples[sel[i]];
+    h_kidx[i] = (uint32_t)t.key_idx; h_didx[i] = t.data_idx; h_tags[i] = t.tag; h_pre[i] = t.pre;
+    h_soff[i] = spos;
+    if (!whole) {
+      memcpy(h_sig + i * (size_t)kb, pl.sig_blob.data() + t.sig_pos, kb);
+      if (t.suffix_len) memcpy(h_suf + spos, pl.suffix_blob.data() + t.suffix_pos, t.suffix_len);
+    }
+    spos += t.suffix_len;
+  }
+  h_soff[nt] = spos;
+  rc = a.upload();
   if (rc) return rc;
   CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, nt, d_dig, d_tags, d_pre, a.stream()));
-  { std::lock_guard<std::mutex> g(e->mu); e->stats.launches += 1; }
+  { std::lock_guard<std::mutex> lk(e->mu); e->stats.launches += 1; }
   if (alg == 19) {
     const int block = 128;
     bftq::ecdsa_p256_verify_kernel<<<(unsigned)((nt + block - 1) / block), block, 0, a.stream()>>>(
         d_sig, 0, nullptr, d_sig, d_sig + 32, d_dig, (uint32_t)dlen, nt, d_pre, d_st);
     CU(cudaGetLastError());
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> lk(e->mu);
     e->stats.launches += 1;
     e->stats.items += nt;
   } else if (alg == 17) {
@@ -1392,22 +1491,46 @@ int run_plan_group(bftq_engine* e, Plan& pl, const std::vector<uint32_t>& sel, u
     rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream(), kb);
     if (rc) return rc;
   }
-  rc = a.download();
-  if (rc) return rc;
-  for (size_t i = 0; i < nt; i++) status[sel[i]] = st[i];
-  return BFTQ_OK;
+  return a.download_async();
 }
 
-int run_plan(bftq_engine* e, Plan& pl, std::vector<uint8_t>& status) {
-  status.assign(pl.tuples.size(), 0);
-  std::map<std::tuple<uint32_t, int, int>, std::vector<uint32_t>> groups;    // (hash algorithm, signature algorithm, key-size class)
-  for (size_t i = 0; i < pl.tuples.size(); i++)
-    groups[std::make_tuple((uint32_t)pl.tuples[i].hash_id, (int)pl.tuples[i].alg, (int)pl.tuples[i].kbytes)].push_back((uint32_t)i);
-  for (auto& g : groups) {
-    int rc = run_plan_group(e, pl, g.second, std::get<0>(g.first), std::get<1>(g.first), std::get<2>(g.first), status);
-    if (rc) return rc;
+int group_finish(GroupRun& g, std::vector<uint8_t>& status) {
+  if (!g.arena) return BFTQ_OK;
+  int rc = g.arena->finish();
+  for (size_t i = 0; i < g.sel.size(); i++) status[g.sel[i]] = g.st[i];
+  g.arena.reset();
+  return rc;
+}
+
+// A plan (one chunk of a batch call) on the device: its groups run on one stream each.
+struct PlanRun {
+  Plan pl;
+  std::vector<GroupRun> groups;
+  std::vector<uint8_t> status;               // per tuple, BFTQ_ST_*
+  uint64_t lo = 0, hi = 0;                   // the batch items [lo, hi) this plan covers
+};
+
+void split_groups(PlanRun& pr) {
+  const Plan& pl = pr.pl;
+  pr.groups.clear();
+  pr.status.assign(pl.tuples.size(), 0);
+  for (size_t i = 0; i < pl.tuples.size(); i++) {
+    const Tuple& t = pl.tuples[i];
+    GroupRun* g = nullptr;
+    for (auto& c : pr.groups) if (c.hash_alg == t.hash_id && c.alg == (int)t.alg && c.kb == (int)t.kbytes) { g = &c; break; }
+    if (!g) { pr.groups.emplace_back(); g = &pr.groups.back(); g->hash_alg = t.hash_id; g->alg = t.alg; g->kb = (int)t.kbytes; }
+    g->sel.push_back((uint32_t)i);
   }
+}
+int plan_enqueue(bftq_engine* e, PlanRun& pr, bool sleepy) {
+  split_groups(pr);
+  for (auto& g : pr.groups) { int rc = group_enqueue(e, pr.pl, g, pr.status, sleepy); if (rc) return rc; }
   return BFTQ_OK;
+}
+int plan_finish(PlanRun& pr) {
+  int rc = BFTQ_OK;
+  for (auto& g : pr.groups) { int r = group_finish(g, pr.status); if (r && !rc) rc = r; }
+  return rc;
 }
 
 // Per item: did call c succeed (any candidate tuple verified) and who signed.
@@ -1420,6 +1543,98 @@ void fold_calls(const Plan& pl, const std::vector<uint8_t>& status, std::vector<
     CallResult& cr = out[tp.item][tp.call];
     if (!cr.ok && status[t] == 0) { cr.ok = true; cr.signer = tp.signer_id; }
   }
+}
+
+// Host threads a batch call may use: the CPU quota of the container (not the core count of the box),
+// capped at 16; BFTQ_HOST_THREADS overrides.  Chunk = items per plan; BFTQ_PLAN_CHUNK overrides.
+unsigned packer_threads() {
+  if (const char* s = getenv("BFTQ_HOST_THREADS")) { const int x = atoi(s); if (x > 0) return (unsigned)std::min(x, 64); }
+  static const unsigned n = [] {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char q[32]; unsigned long per = 0;
+      if (fscanf(f, "%31s %lu", q, &per) == 2 && strcmp(q, "max") != 0 && per) hw = std::min<unsigned>(hw, (unsigned)std::max(1L, (long)((atol(q) + per / 2) / per)));
+      fclose(f);
+    }
+    return std::min(hw, 16u);
+  }();
+  return n;
+}
+uint64_t packer_chunk() {
+  if (const char* s = getenv("BFTQ_PLAN_CHUNK")) { const long x = atol(s); if (x > 0) return (uint64_t)x; }
+  return 0;                 // 0: sized per call (run_batch)
+}
+
+// The packer's batch driver.  The batch is cut into chunks of packer_chunk() items; worker threads take
+// chunks off a shared counter, and each keeps two plans going: while the kernels of chunk c run on its
+// stream the thread parses chunk c+1, so packet parsing (CPU) and digest + verify (GPU) overlap both
+// across and inside threads.  build(lo, hi, plan) parses the items, done(planrun) folds the statuses
+// into the caller's outputs (disjoint item ranges, so no locking).  e == nullptr: parse only.
+template <typename Build, typename Done>
+int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build build, Done done) {
+  unsigned want = max_threads ? max_threads : packer_threads();
+  // Concurrent batch calls share the host: a call starts only as many workers as the budget has left
+  // (at least one), so four callers do not put 64 threads on 16 cores.
+  int taken = 0;
+  if (e && !max_threads) {
+    const int budget = (int)want;
+    int cur = e->packer_workers.load();
+    for (;;) {
+      taken = std::max(1, budget - cur);
+      if (e->packer_workers.compare_exchange_weak(cur, cur + taken)) break;
+    }
+    want = (unsigned)taken;
+  }
+  // Chunk size: small enough that every worker gets several chunks (so its parsing overlaps the kernels
+  // of its previous chunks and the GPU starts early), large enough to amortise the per-chunk driver calls.
+  uint64_t chunk = packer_chunk();
+  if (!chunk) chunk = std::min<uint64_t>(4096, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * 4) + 63) / 64) * 64));
+  const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
+  const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, n_chunks));
+  const bool sleepy = [] { const char* v = getenv("BFTQ_SPIN_SYNC"); return !(v && atoi(v) > 0); }();
+  std::atomic<uint64_t> next{0};
+  std::atomic<int> first_err{BFTQ_OK};
+  std::mutex err_mu;
+  std::string err_text;
+  auto worker = [&]() {
+    if (e) cudaSetDevice(e->device);
+    constexpr int kDepth = 4;                    // plans a worker keeps in flight
+    PlanRun runs[kDepth];
+    uint64_t head = 0, tail = 0;                 // runs[tail % kDepth .. head % kDepth) are in flight
+    auto note = [&](int rc) {
+      if (!rc) return;
+      std::lock_guard<std::mutex> lk(err_mu);
+      if (first_err.load() == BFTQ_OK) { first_err.store(rc); err_text = g_last_error; }
+    };
+    auto retire = [&]() {
+      PlanRun& pv = runs[tail % kDepth];
+      if (e) note(plan_finish(pv));
+      if (first_err.load() == BFTQ_OK) done(pv);
+      tail++;
+    };
+    for (;;) {
+      const uint64_t c = next.fetch_add(1);
+      if (c >= n_chunks || first_err.load() != BFTQ_OK) break;
+      if (head - tail == kDepth) retire();
+      PlanRun& pr = runs[head % kDepth];
+      pr.lo = c * chunk; pr.hi = std::min(n_items, pr.lo + chunk);
+      pr.pl.reset();
+      build(pr.lo, pr.hi, pr.pl);
+      if (e) note(plan_enqueue(e, pr, sleepy)); else split_groups(pr);
+      head++;
+    }
+    while (tail < head) retire();
+    for (auto& r : runs) for (auto& g : r.groups) if (g.arena) g.arena->finish();      // error path: let in-flight copies land
+  };
+  if (nthreads <= 1) worker();
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  if (taken) e->packer_workers.fetch_sub(taken);
+  if (first_err.load() != BFTQ_OK) return fail(first_err.load(), err_text);
+  return BFTQ_OK;
 }
 
 int check_blobs(const void* blob, const uint64_t* off, uint64_t n) {
@@ -1497,45 +1712,54 @@ int bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids
 
 static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
                              const uint64_t* sig_off, const uint8_t* cert_blob, const uint64_t* cert_off, uint64_t n_items,
-                             int32_t* out_err) {
-  if (!kr || !out_err) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
+                             int32_t* out_err, bool parse_only = false, unsigned threads = 0, uint64_t* n_tuples = nullptr) {
+  if (!kr || (!out_err && !parse_only)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!kr->e && !parse_only) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
   if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(sig_blob, sig_off, n_items) || (cert_off && check_blobs(cert_blob, cert_off, n_items)))
     return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
   if (n_items == 0) return BFTQ_OK;
-  Plan pl;
-  pl.data_off.push_back(0);
-  std::vector<std::vector<pg::Entity>> cert_rings;          // one single-entity ring per item (VerifyWithCertificate)
-  std::vector<pg::Entity> sec, pub;
-  if (cert_off) {
-    cert_rings.resize(n_items);
-    for (uint64_t i = 0; i < n_items; i++) {
-      std::vector<pg::Entity> ents;
-      pg::read_entities(cert_blob + cert_off[i], (size_t)(cert_off[i + 1] - cert_off[i]), ents);
-      if (!ents.empty()) { index_entity_keys(kr->e, ents[0]); cert_rings[i].push_back(ents[0]); }
-    }
-  } else {
-    std::lock_guard<std::mutex> g(kr->mu);
-    sec = kr->secring; pub = kr->keyring;
-  }
-  for (uint64_t i = 0; i < n_items; i++) {
+  std::vector<pg::Entity> sec, pub;                         // snapshot: Register / Remove may run concurrently (crypto_pgp.go:142-177)
+  if (!cert_off) { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
+  const std::vector<const std::vector<pg::Entity>*> shared_rings = {&sec, &pub};
+  std::atomic<uint64_t> tuples{0};
+  auto build = [&](uint64_t lo, uint64_t hi, Plan& pl) {
+    std::vector<pg::Entity> cert_ring;                      // VerifyWithCertificate: a one-entity ring per item
     std::vector<const std::vector<pg::Entity>*> rings;
-    if (cert_off) rings = {&cert_rings[i]}; else rings = {&sec, &pub};
-    plan_item(pl, (uint32_t)i, tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), sig_blob + sig_off[i],
-              (size_t)(sig_off[i + 1] - sig_off[i]), rings, false);
-  }
-  std::vector<uint8_t> status;
-  int rc = run_plan(kr->e, pl, status);
-  if (rc) return rc;
-  std::vector<std::vector<CallResult>> calls;
-  fold_calls(pl, status, calls);
-  for (uint64_t i = 0; i < n_items; i++) {
-    bool ok = !pl.item_failed[i] && !calls[i].empty();       // "at least we need one valid signature"
-    for (auto& c : calls[i]) ok = ok && c.ok;
-    if (cert_off && cert_rings[i].empty()) ok = false;
-    out_err[i] = ok ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
-  }
-  return BFTQ_OK;
+    for (uint64_t i = lo; i < hi; i++) {
+      if (cert_off) {
+        cert_ring.clear();
+        std::vector<pg::Entity> ents;
+        pg::read_entities(cert_blob + cert_off[i], (size_t)(cert_off[i + 1] - cert_off[i]), ents);
+        if (!ents.empty()) { index_entity_keys(kr->e, ents[0]); cert_ring.push_back(ents[0]); }
+        rings = {&cert_ring};
+      }
+      // (the per-item ring dies with this iteration: a plan keeps copies, never pointers into it; an
+      // empty ring makes every issuer unknown, i.e. the item fails like a missing certificate must)
+      plan_item(pl, (uint32_t)(i - lo), tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), sig_blob + sig_off[i],
+                (size_t)(sig_off[i + 1] - sig_off[i]), cert_off ? rings : shared_rings, false);
+    }
+    tuples.fetch_add(pl.tuples.size());
+  };
+  auto done = [&](PlanRun& pr) {
+    if (!out_err) return;
+    const Plan& pl = pr.pl;
+    const size_t n = (size_t)(pr.hi - pr.lo);
+    // Verify: every call must succeed and there must be at least one ("at least we need one valid signature")
+    std::vector<uint8_t> call_ok;
+    std::vector<uint32_t> call_base(n + 1, 0);
+    for (size_t i = 0; i < n; i++) call_base[i + 1] = call_base[i] + pl.calls_per_item[i];
+    call_ok.assign(call_base[n], 0);
+    for (size_t t = 0; t < pl.tuples.size(); t++)
+      if (pr.status[t] == 0) call_ok[call_base[pl.tuples[t].item] + pl.tuples[t].call] = 1;
+    for (size_t i = 0; i < n; i++) {
+      bool ok = !pl.item_failed[i] && pl.calls_per_item[i] > 0;
+      for (uint32_t c = call_base[i]; c < call_base[i + 1]; c++) ok = ok && call_ok[c];
+      out_err[pr.lo + i] = ok ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
+    }
+  };
+  int rc = run_batch(parse_only ? nullptr : kr->e, n_items, threads, build, done);
+  if (n_tuples) *n_tuples = tuples.load();
+  return rc;
 }
 
 int bftq_signature_parse(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, int collective, uint64_t* out_issuers,
@@ -1575,6 +1799,14 @@ int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_b
                                           const uint64_t* cert_off, uint64_t n_items, int32_t* out_err) {
   if (!cert_off) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   return verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, cert_blob, cert_off, n_items, out_err);
+}
+
+int bftq_signature_plan_measure(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
+                                const uint64_t* sig_off, uint64_t n_items, uint32_t threads, uint64_t* n_tuples, double* seconds) {
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, nullptr, nullptr, n_items, nullptr, true, threads, n_tuples);
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 // Signers(): every parseable v4 signature packet whose issuer is a PRIMARY key id of the keyring.
@@ -1644,20 +1876,21 @@ int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uin
   if (n_items == 0) return BFTQ_OK;
   std::vector<pg::Entity> sec, pub;
   { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
-  std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
-  Plan pl;
-  pl.data_off.push_back(0);
-  for (uint64_t i = 0; i < n_items; i++)
-    plan_item(pl, (uint32_t)i, tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), ss_blob + ss_off[i],
-              (size_t)(ss_off[i + 1] - ss_off[i]), rings, true);
-  std::vector<uint8_t> status;
-  int rc = run_plan(kr->e, pl, status);
-  if (rc) return rc;
-  std::vector<std::vector<CallResult>> calls;
-  fold_calls(pl, status, calls);
+  const std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
   std::vector<std::vector<uint64_t>> signers(n_items);
-  for (uint64_t i = 0; i < n_items; i++)
-    for (auto& c : calls[i]) if (c.ok) signers[i].push_back(c.signer);      // no dedupe (crypto_pgp.go:492)
+  auto build = [&](uint64_t lo, uint64_t hi, Plan& pl) {
+    for (uint64_t i = lo; i < hi; i++)
+      plan_item(pl, (uint32_t)(i - lo), tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), ss_blob + ss_off[i],
+                (size_t)(ss_off[i + 1] - ss_off[i]), rings, true);
+  };
+  auto done = [&](PlanRun& pr) {
+    std::vector<std::vector<CallResult>> calls;
+    fold_calls(pr.pl, pr.status, calls);
+    for (size_t i = 0; i < calls.size(); i++)
+      for (auto& c : calls[i]) if (c.ok) signers[pr.lo + i].push_back(c.signer);      // no dedupe (crypto_pgp.go:492)
+  };
+  int rc = run_batch(kr->e, n_items, 0, build, done);
+  if (rc) return rc;
   std::vector<uint8_t> bits;
   rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
   if (rc) return rc;

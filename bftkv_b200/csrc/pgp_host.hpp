@@ -83,6 +83,12 @@ inline int read_packet(Reader& r, int& tag, const uint8_t*& body, size_t& blen, 
   }
 }
 
+struct Span {
+  const uint8_t* p = nullptr; size_t n = 0;
+  const uint8_t* data() const { return p; }
+  size_t size() const { return n; }
+};
+
 struct SigPacket {
   int version = 0;
   uint8_t sig_type = 0, pk_algo = 0, hash_id = 0;
@@ -92,9 +98,15 @@ struct SigPacket {
   int is_primary_id = -1;                 // -1 absent
   bool has_revocation_reason = false;
   uint8_t hash_tag[2] = {0, 0};
-  std::vector<uint8_t> suffix;            // bytes hashed after the data (incl. trailer)
-  std::vector<uint8_t> mpi;               // RSA signature MPI bytes (leading zeros stripped as stored)
-  std::vector<uint8_t> r, s;              // DSA / ECDSA signature MPIs, leading zeros stripped
+  // Views into the packet body handed to parse_signature (valid until the reader moves on): the packer
+  // parses tens of millions of these per second, so nothing here allocates.
+  Span hashed;                            // bytes hashed after the data: v4 = version..end of hashed area, v3 = type + time
+  uint8_t trailer[6] = {0, 0, 0, 0, 0, 0};
+  uint8_t trailer_len = 0;                // v4: 04 FF len32 follows the hashed area; v3: nothing
+  Span mpi;                               // RSA signature MPI bytes (as stored)
+  Span r, s;                              // DSA / ECDSA signature MPIs, leading zeros stripped
+  size_t suffix_size() const { return hashed.n + trailer_len; }
+  void write_suffix(uint8_t* out) const { if (hashed.n) memcpy(out, hashed.p, hashed.n); memcpy(out + hashed.n, trailer, trailer_len); }
 };
 
 inline int parse_subpackets(const uint8_t* a, size_t n, SigPacket& s, bool hashed) {
@@ -147,12 +159,12 @@ inline int parse_signature(const uint8_t* b, size_t n, SigPacket& s) {
     s.has_ctime = true;
     if (s.pk_algo != 1 && s.pk_algo != 3 && s.pk_algo != 17) return kUnsupported;
     if (!hash_digest_len(s.hash_id)) return kUnsupported;
-    s.suffix.assign(b + 2, b + 7);
+    s.hashed = Span{b + 2, 5};
     s.hash_tag[0] = b[17]; s.hash_tag[1] = b[18];
     if (s.pk_algo == 1 || s.pk_algo == 3) {
       size_t p = 19; const uint8_t* md; size_t ml; unsigned bits;
       if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
-      s.mpi.assign(md, md + ml);
+      s.mpi = Span{md, ml};
     }
     return kOk;
   }
@@ -164,9 +176,10 @@ inline int parse_signature(const uint8_t* b, size_t n, SigPacket& s) {
   const size_t hl = ((size_t)b[4] << 8) | b[5];
   if (6 + hl + 2 > n) return kStructural;
   const size_t l = 6 + hl;
-  s.suffix.assign(b, b + l);
-  const uint8_t trailer[6] = {0x04, 0xff, (uint8_t)(l >> 24), (uint8_t)(l >> 16), (uint8_t)(l >> 8), (uint8_t)l};
-  s.suffix.insert(s.suffix.end(), trailer, trailer + 6);
+  s.hashed = Span{b, l};
+  s.trailer[0] = 0x04; s.trailer[1] = 0xff; s.trailer[2] = (uint8_t)(l >> 24); s.trailer[3] = (uint8_t)(l >> 16);
+  s.trailer[4] = (uint8_t)(l >> 8); s.trailer[5] = (uint8_t)l;
+  s.trailer_len = 6;
   int rc = parse_subpackets(b + 6, hl, s, true);
   if (rc) return rc;
   size_t p = 6 + hl;
@@ -181,13 +194,13 @@ inline int parse_signature(const uint8_t* b, size_t n, SigPacket& s) {
   p += 2;
   const uint8_t* md; size_t ml; unsigned bits;
   if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
-  if (s.pk_algo == 1 || s.pk_algo == 3) s.mpi.assign(md, md + ml);
+  if (s.pk_algo == 1 || s.pk_algo == 3) s.mpi = Span{md, ml};
   else {                                                           // DSA/ECDSA: r and s must be well formed
     while (ml && *md == 0) { md++; ml--; }
-    s.r.assign(md, md + ml);
+    s.r = Span{md, ml};
     if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
     while (ml && *md == 0) { md++; ml--; }
-    s.s.assign(md, md + ml);
+    s.s = Span{md, ml};
   }
   return kOk;
 }

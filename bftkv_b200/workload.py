@@ -116,3 +116,88 @@ def make_read_ops(pool, n_ops: int, n_replicas: int, seed: int = 0xBF7C0004, p_o
     op_off = (np.arange(M + 1, dtype=np.uint64) * R).astype(np.uint32)
     return {"op_off": op_off, "key_idx": key_idx, "sig": sig, "digest": digest, "pre_status": pre, "ts": ts,
             "value_id": value_id, "expect_status": expect}
+
+
+# ---- OpenPGP-packet form of config 2: what crypto.Signature.Verify actually receives -----------------
+
+def _mpi(x: int) -> bytes:
+    return struct.pack(">H", x.bit_length()) + x.to_bytes((x.bit_length() + 7) // 8, "big")
+
+
+def _old_packet(tag: int, body: bytes) -> bytes:
+    """Old-format header with a 2-octet length (what GnuPG writes for keys and signatures)."""
+    if tag == 13 and len(body) < 256:
+        return bytes([0x80 | (tag << 2) | 0, len(body)]) + body
+    return bytes([0x80 | (tag << 2) | 1]) + struct.pack(">H", len(body)) + body
+
+
+def pgp_key_id(pub_body: bytes) -> int:
+    """Low 64 bits of SHA-1(0x99 || len16 || public-key packet body) (RFC 4880 §12.2)."""
+    return int.from_bytes(hashlib.sha1(b"\x99" + struct.pack(">H", len(pub_body)) + pub_body).digest()[12:], "big")
+
+
+def _v4_sig_packet(priv, key_id: int, sig_type: int, hashed_prefix: bytes, ctime: int, extra_hashed: bytes = b"") -> bytes:
+    """A v4 RSA/SHA-256 signature packet over `hashed_prefix` (the bytes hashed before the signature's
+    own hashed area), RFC 4880 §5.2.3/§5.2.4: hashed = creation time (+ extra), unhashed = issuer."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding
+    from cryptography.hazmat.primitives.asymmetric.utils import Prehashed
+    hashed = bytes([5, 2]) + struct.pack(">I", ctime) + extra_hashed
+    head = bytes([4, sig_type, 1, 8]) + struct.pack(">H", len(hashed)) + hashed
+    digest = hashlib.sha256(hashed_prefix + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
+    s = int.from_bytes(priv.sign(digest, padding.PKCS1v15(), Prehashed(hashes.SHA256())), "big")
+    unhashed = bytes([9, 16]) + struct.pack(">Q", key_id)
+    return _old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + digest[:2] + _mpi(s))
+
+
+def pgp_public_key_block(k, priv, uid: bytes, ctime: int = 0x5E000000):
+    """Transferable public key: public-key packet, user id, positive self-certification with key
+    flags certify|sign.  Returns (block bytes, key id)."""
+    body = bytes([4]) + struct.pack(">I", ctime) + bytes([1]) + _mpi(k["n"]) + _mpi(k["e"])
+    kid = pgp_key_id(body)
+    prefix = b"\x99" + struct.pack(">H", len(body)) + body + b"\xb4" + struct.pack(">I", len(uid)) + uid
+    selfsig = _v4_sig_packet(priv, kid, 0x13, prefix, ctime, extra_hashed=bytes([2, 27, 0x03]))
+    return _old_packet(6, body) + _old_packet(13, uid) + selfsig, kid
+
+
+def make_pgp_verify_batch(n_items: int, n_keys: int = 16, seed: int = 0xBF7C0002, corrupt_rate: float = 0.01,
+                          unknown_rate: float = 0.001, corrupt_seed: int = 0xBF7C0003, threads: int = 0):
+    """Config 2 in the form crypto.Signature.Verify sees it (crypto_pgp.go:319-330): tbs_i =
+    packet.Serialize(x_i, v_i, t=i) and sig_i = ONE detached OpenPGP v4 RSA-2048/SHA-256 signature
+    packet (binary, type 0x00) by key key_idx[i]; a seeded fraction has a flipped bit in the signature
+    MPI (-> ErrInvalidSignature) or is issued by a key outside the keyring (-> ErrUnknownIssuer, which
+    Verify also reports as ErrInvalidSignature).  Returns dict(keyring=public key blocks of the n_keys
+    keys, key_ids, tbs=[bytes], sigs=[bytes], expect_ok bool[N], key_idx)."""
+    keys = load_keys(n_keys + 1)                      # the extra key signs the "unknown issuer" items
+    privs = [_private_key(k) for k in keys]
+    blocks, kids = [], []
+    for i, k in enumerate(keys):
+        b, kid = pgp_public_key_block(k, privs[i], b"bftq-node-%02d <n%02d@bftq.test>" % (i, i))
+        blocks.append(b); kids.append(kid)
+    rng = np.random.default_rng(seed)
+    key_idx = rng.integers(0, n_keys, n_items).astype(np.uint32)
+    xv = rng.integers(0, 256, (n_items, 48), dtype=np.uint8)
+    crng = np.random.default_rng(corrupt_seed)
+    bad = crng.random(n_items) < corrupt_rate
+    bad_byte = crng.integers(0, 200, n_items)
+    bad_bit = crng.integers(0, 8, n_items)
+    unk = crng.random(n_items) < unknown_rate
+    tbs = [None] * n_items
+    sigs = [None] * n_items
+    threads = threads or min(32, os.cpu_count() or 1)
+
+    def work(lo_hi):
+        lo, hi = lo_hi
+        for i in range(lo, hi):
+            m = tbs_packet(xv[i, :16].tobytes(), xv[i, 16:].tobytes(), i)
+            ki = n_keys if unk[i] else int(key_idx[i])
+            pkt = bytearray(_v4_sig_packet(privs[ki], kids[ki], 0x00, m, 0x5F000000 + (i & 0xFFFF)))
+            if bad[i]:
+                pkt[len(pkt) - 1 - int(bad_byte[i])] ^= 1 << int(bad_bit[i])      # inside the 256-byte MPI
+            tbs[i], sigs[i] = m, bytes(pkt)
+
+    step = max(1, (n_items + threads * 4 - 1) // (threads * 4))
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, [(lo, min(n_items, lo + step)) for lo in range(0, n_items, step)]))
+    return {"keyring": b"".join(blocks[:n_keys]), "key_ids": kids[:n_keys], "outsider_block": blocks[n_keys],
+            "tbs": tbs, "sigs": sigs, "expect_ok": ~(bad | unk), "key_idx": key_idx}

@@ -305,6 +305,14 @@ int bftq_signature_verify_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const
 int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
                                           const uint8_t* sig_blob, const uint64_t* sig_off, const uint8_t* cert_blob,
                                           const uint64_t* cert_off, uint64_t n_items, int32_t* out_err);
+/* Diagnostic: runs ONLY the host half of bftq_signature_verify_batch (packet parsing, keyring lookup,
+ * tuple composition; `threads` = 0 picks the library default, BFTQ_HOST_THREADS) and reports the number
+ * of (signature, candidate key) tuples it would send to the GPU and the wall time.  No verification
+ * happens and no result is produced; works on a parse-only keyring.  Used to size the host side of the
+ * path against the kernels (bench.py `packer`). */
+int bftq_signature_plan_measure(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
+                                const uint64_t* sig_off, uint64_t n_items, uint32_t threads, uint64_t* n_tuples, double* seconds);
+
 /* PGPSignature.Signers (crypto_pgp.go:373-390) for one SignaturePacket.Data: key ids of the
  * issuers present in the keyring (primary ids via getCertById), duplicates kept, in packet order. */
 int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n);

@@ -2,6 +2,8 @@
 entry points of libbftq): Signature.Verify / VerifyWithCertificate / Signers and
 CollectiveSignature.Verify / Combine decisions must equal the oracle's restatement of
 crypto/pgp/crypto_pgp.go:319-344,373-390,485-515 on GnuPG-made inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,43 @@ def test_aggregator_coalesces_concurrent_verifies(env, golden):
     st = bs.stats()
     assert st["items"] == 512 and st["batches"] <= 64, st
     bs.close()
+
+
+# ---- the chunked, multi-threaded packer (bftq_signature_verify_batch over a big batch) ---------------
+
+def _pgp_batch(n, **kw):
+    from bftkv_b200 import workload
+    return workload.make_pgp_verify_batch(n, **kw)
+
+
+def test_signature_verify_big_batch_chunked_threads():
+    """20 000 detached OpenPGP signatures through Signature.Verify's batch form: several chunks per
+    worker thread, several threads; decisions equal the generator's ground truth and (on a sample) the
+    oracle's restatement of crypto_pgp.go:319-330.  Also with chunk boundaries that split unevenly."""
+    w = _pgp_batch(20000, n_keys=16)
+    eng = Engine(0)
+    kr = Keyring(eng)
+    kr.register(w["keyring"])
+    sig = Signature(kr)
+    ring = pgp.read_entities(w["keyring"])
+    for chunk, threads in ((None, None), ("777", "5"), ("30000", "1")):
+        if chunk:
+            os.environ["BFTQ_PLAN_CHUNK"], os.environ["BFTQ_HOST_THREADS"] = chunk, threads
+        try:
+            got = sig.verify_batch(w["tbs"], w["sigs"])
+        finally:
+            os.environ.pop("BFTQ_PLAN_CHUNK", None), os.environ.pop("BFTQ_HOST_THREADS", None)
+        ok = np.array([g is None for g in got])
+        assert np.array_equal(ok, w["expect_ok"]), (chunk, threads, int(np.sum(ok != w["expect_ok"])))
+    for i in list(range(0, 20000, 397)) + [int(j) for j in np.nonzero(~w["expect_ok"])[0][:40]]:
+        assert (pgp.signature_verify(ring, w["tbs"][i], w["sigs"][i]) is None) == bool(ok[i])
+    # an outsider becomes a known issuer once its key block is registered
+    bad = [int(j) for j in np.nonzero(~w["expect_ok"])[0]]
+    kr.register(w["outsider_block"])
+    got2 = sig.verify_batch([w["tbs"][j] for j in bad], [w["sigs"][j] for j in bad])
+    ring2 = pgp.read_entities(w["keyring"] + w["outsider_block"])
+    for j, g in zip(bad, got2):
+        assert (g is None) == (pgp.signature_verify(ring2, w["tbs"][j], w["sigs"][j]) is None)
+    assert any(g is None for g in got2)
+    kr.close()
+    eng.close()

@@ -108,3 +108,32 @@ def test_pure_garbage_never_crashes(env):
         data = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 600)))
         for collective in (False, True):
             assert sig.parse(data, collective) == oracle_walk(ents, data, collective)
+
+
+def test_plan_measure_counts_tuples_like_the_oracle(built):
+    """Host half of the batch verify only (no GPU): the number of (signature packet, candidate key)
+    tuples the chunked, multi-threaded packer composes equals the oracle's count of known-issuer
+    packets, whatever the thread / chunk split."""
+    import ctypes as C
+    import os
+    from bftkv_b200 import _lib, workload
+    from bftkv_b200.crypto_gpu import _blob
+    w = workload.make_pgp_verify_batch(3000, n_keys=5, corrupt_rate=0.02, unknown_rate=0.03)
+    ents = pgp.read_entities(w["keyring"])
+    expect = sum(len(oracle_walk(ents, s, False)[0]) for s in w["sigs"])
+    assert 0 < expect < 3000                                   # some issuers are outside the keyring
+    kr = Keyring(None)
+    assert kr.register(w["keyring"]) == 5
+    lib = _lib.load()
+    tb, to = _blob(w["tbs"])
+    sb, so = _blob(w["sigs"])
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    for threads, chunk in ((1, "100000"), (3, "257"), (8, "64")):
+        os.environ["BFTQ_PLAN_CHUNK"] = chunk
+        try:
+            nt, sec = C.c_uint64(), C.c_double()
+            _lib.check(lib.bftq_signature_plan_measure(kr._h, p(tb), p(to), p(sb), p(so), len(w["tbs"]), threads, C.byref(nt), C.byref(sec)))
+        finally:
+            del os.environ["BFTQ_PLAN_CHUNK"]
+        assert nt.value == expect, (threads, chunk, nt.value, expect)
+    kr.close()

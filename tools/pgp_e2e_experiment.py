@@ -1,0 +1,70 @@
+"""Packet-level end-to-end sweep on one GPU: bftq_signature_verify_batch over the OpenPGP form of BASELINE
+configs[1] under different chunk sizes / worker-thread counts / concurrent callers.
+python tools/pgp_e2e_experiment.py > gpurun_out/pgp_e2e_experiment.json"""
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from bftkv_b200 import Engine, _lib, workload
+from bftkv_b200.crypto_gpu import Keyring, _blob
+
+N = 65536
+
+
+def main():
+    w = workload.make_pgp_verify_batch(N)
+    eng = Engine(0)
+    kr = Keyring(eng)
+    kr.register(w["keyring"])
+    lib = _lib.load()
+    tb, to = _blob(w["tbs"])
+    sb, so = _blob(w["sigs"])
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    rows = []
+
+    def run(chunk, threads, callers, steps=12):
+        if chunk:
+            os.environ["BFTQ_PLAN_CHUNK"] = str(chunk)
+        else:
+            os.environ.pop("BFTQ_PLAN_CHUNK", None)
+        os.environ["BFTQ_HOST_THREADS"] = str(threads)
+        errs = [np.zeros(N, np.int32) for _ in range(callers)]
+
+        def caller(c, n):
+            for _ in range(n):
+                _lib.check(lib.bftq_signature_verify_batch(kr._h, p(tb), p(to), p(sb), p(so), N, p(errs[c])))
+        for c in range(callers):
+            caller(c, 2)
+        share = [steps // callers + (1 if c < steps % callers else 0) for c in range(callers)]
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=caller, args=(c, share[c])) for c in range(callers)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        dt = time.perf_counter() - t0
+        for c in range(callers):
+            assert np.array_equal(errs[c] == 0, w["expect_ok"])
+        rows.append({"chunk": chunk, "threads": threads, "callers": callers, "verifies_per_sec": N * steps / dt, "ms_per_batch": dt / steps * 1e3})
+        print(rows[-1], file=sys.stderr)
+
+    for spin in ("0", "1"):
+        os.environ["BFTQ_SPIN_SYNC"] = spin
+        for chunk in (0, 512, 1024, 2048, 4096):
+            run(chunk, 16, 1)
+            rows[-1]["spin"] = spin
+        for threads in (4, 8, 12, 16, 24):
+            run(0, threads, 1)
+            rows[-1]["spin"] = spin
+        for callers in (2, 4):
+            run(0, 16, callers)
+            rows[-1]["spin"] = spin
+    print(json.dumps(rows))
+
+
+if __name__ == "__main__":
+    main()
