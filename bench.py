@@ -8,7 +8,9 @@ A "step" = one pass of the hot path over one such batch.  N GPUs = N independent
 the max-over-ranks time).
 
   value     verifies/s, inputs already resident in HBM (device API, CUDA events on the launch stream)
-  e2e       verifies/s through the host C-ABI call with pinned HOST buffers: H2D + kernel + D2H per step
+  e2e       verifies/s through the reference-facing operator: bftq_signature_verify_batch (= crypto.Signature.Verify's
+            batch form) with OpenPGP packets in pageable HOST memory: parse + H2D + K4 + K1 + D2H per step
+  e2e_flat  the same through the flat tuple call (bftq_rsa_verify_batch, pinned host buffers, digests precomputed)
   roofline  integer-ALU bound: 156 864 32x32->64 MACs per verify x verifies / kernel
             time, against the IMAD.WIDE rate measured live on the same GPU (bftq_measure_int_peak)
   cpu_baseline  the oracle's C port of the reference CPU path on the host cores (rank 0, N=1)
@@ -257,28 +259,38 @@ def run_gpu(args, rank, local_rank, world):
     kr.register(pw["keyring"])
     ptb, pto = _blob(pw["tbs"])
     psb, pso = _blob(pw["sigs"])
-    perr = np.zeros(ITEMS, np.int32)
+    PCALLERS = max(1, args.pgp_callers)
+    perr = [np.zeros(ITEMS, np.int32) for _ in range(PCALLERS)]
     vp = lambda a: C.c_void_p(a.ctypes.data)
 
-    def pgp_call():
-        L_.check(eng._lib.bftq_signature_verify_batch(kr._h, vp(ptb), vp(pto), vp(psb), vp(pso), ITEMS, vp(perr)))
-    for _ in range(args.warmup):
-        pgp_call()
+    def pgp_caller(c, n):
+        for _ in range(n):
+            L_.check(eng._lib.bftq_signature_verify_batch(kr._h, vp(ptb), vp(pto), vp(psb), vp(pso), ITEMS, vp(perr[c])))
+    for c in range(PCALLERS):
+        pgp_caller(c, args.warmup)
+    pshare = [args.steps // PCALLERS + (1 if c < args.steps % PCALLERS else 0) for c in range(PCALLERS)]
     st0 = eng.stats()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pgp_call()
+    ths = [threading.Thread(target=pgp_caller, args=(c, pshare[c])) for c in range(PCALLERS)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
     torch.cuda.synchronize(dev)
     pgp_s = time.perf_counter() - t0
     barrier()
     st1 = eng.stats()
-    assert np.array_equal(perr == 0, pw["expect_ok"]), "packet-level results differ from expectation"
+    t0 = time.perf_counter()
+    pgp_caller(0, 3)
+    pgp_single_ms = (time.perf_counter() - t0) / 3 * 1e3
+    for c in range(PCALLERS):
+        assert np.array_equal(perr[c] == 0, pw["expect_ok"]), "packet-level results differ from expectation"
     nt_, sec_ = C.c_uint64(), C.c_double()
     L_.check(eng._lib.bftq_signature_plan_measure(kr._h, vp(ptb), vp(pto), vp(psb), vp(pso), ITEMS, 0, C.byref(nt_), C.byref(sec_)))
     L_.check(eng._lib.bftq_signature_plan_measure(kr._h, vp(ptb), vp(pto), vp(psb), vp(pso), ITEMS, 0, C.byref(nt_), C.byref(sec_)))
     pgp_info = {"h2d": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps, "d2h": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
                 "launches": (st1["launches"] - st0["launches"]) // args.steps, "threads": int(os.environ["BFTQ_HOST_THREADS"]),
+                "chunks": (st1["packer_chunks"] - st0["packer_chunks"]) // args.steps, "callers": PCALLERS, "single_ms": pgp_single_ms,
+                "thread_ms": {k: (st1["packer_%s_ns" % k] - st0["packer_%s_ns" % k]) / args.steps * 1e-6 for k in ("parse", "stage", "wait")},
                 "packer_only_items_per_sec": ITEMS / sec_.value}
     kr.close()
 
@@ -407,17 +419,19 @@ def run_gpu(args, rank, local_rank, world):
                    "per_gpu_batch": ITEMS, "l2": "inputs rotated over %d distinct device copies (%d MB > 126 MB L2)"
                    % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4")), "streams_in_flight": NSTREAMS},
         "gpu_launches": int(gpu_launches),
-        "e2e": {"value": e2e_v, "unit": "verifies/s", "h2d_bytes_per_step": ITEMS * (256 + 32 + 4), "d2h_bytes_per_step": ITEMS,
-                "api": "bftq_rsa_verify_batch (host C ABI, pinned host buffers), %d concurrent callers" % NCALLERS,
-                "ms_per_step": e2e_ms / args.steps, "h2d_gbps_this_box": h2d_gbps,
-                "copy_bound_verifies_per_sec": h2d_gbps * 1e9 / (256 + 32 + 4)},
-        "e2e_pgp": {"value": total_items / (pgp_ms * 1e-3), "unit": "verifies/s", "ms_per_step": pgp_ms / args.steps,
-                    "api": "bftq_signature_verify_batch = crypto.Signature.Verify's batch form: OpenPGP signature packets + signed bytes in "
-                           "pageable host memory, error codes out; packet parsing, K4 digest, K1 verify and all copies inside the timed region",
-                    "h2d_bytes_per_step": int(pgp_info["h2d"]), "d2h_bytes_per_step": int(pgp_info["d2h"]),
-                    "kernels_per_step": int(pgp_info["launches"]), "host_threads": pgp_info["threads"],
-                    "copy_bound_verifies_per_sec": h2d_gbps * 1e9 / (pgp_info["h2d"] / ITEMS),
-                    "packer_only_items_per_sec": pgp_info["packer_only_items_per_sec"]},
+        "e2e": {"value": total_items / (pgp_ms * 1e-3), "unit": "verifies/s", "ms_per_step": pgp_ms / args.steps,
+                "h2d_bytes_per_step": int(pgp_info["h2d"]), "d2h_bytes_per_step": int(pgp_info["d2h"]),
+                "api": "bftq_signature_verify_batch = crypto.Signature.Verify's batch form (crypto_pgp.go:319-330): OpenPGP signature packets + "
+                       "signed bytes in pageable host memory in, error codes out; packet parsing, keyring lookup, K4 digest + hash-tag check, K1 "
+                       "verify and every copy inside the timed region; %d concurrent callers (one batch each per step)" % pgp_info["callers"],
+                "one_caller_ms_per_batch": pgp_info["single_ms"],
+                "kernels_per_step": int(pgp_info["launches"]), "host_threads": pgp_info["threads"], "chunks_per_step": int(pgp_info["chunks"]),
+                "worker_thread_ms_per_step": pgp_info["thread_ms"], "packer_only_items_per_sec": pgp_info["packer_only_items_per_sec"],
+                "h2d_gbps_this_box": h2d_gbps, "copy_bound_verifies_per_sec": h2d_gbps * 1e9 / (pgp_info["h2d"] / ITEMS)},
+        "e2e_flat": {"value": e2e_v, "unit": "verifies/s", "h2d_bytes_per_step": ITEMS * (256 + 32 + 4), "d2h_bytes_per_step": ITEMS,
+                     "api": "bftq_rsa_verify_batch (flat tuples: key index, padded signature, precomputed digest; pinned host buffers), "
+                            "%d concurrent callers" % NCALLERS,
+                     "ms_per_step": e2e_ms / args.steps},
         "quorum_ops": {"metric": "quorum_certified_read_ops_per_sec", "value": M * world * qsteps / (q_ms * 1e-3), "unit": "ops/s",
                        "verifies_per_sec": NQ * world * qsteps / (q_ms * 1e-3), "steps": qsteps, "ms_per_step": q_ms / qsteps,
                        "config": {"workload": "batch 65536 read ops x 16-replica quorum, verify + wotqs read tally (BASELINE configs[2])",
@@ -458,7 +472,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--copies", type=int, default=8)
     ap.add_argument("--streams", type=int, default=2, help="streams the device-resident launches alternate over")
-    ap.add_argument("--callers", type=int, default=4, help="concurrent host callers in the end-to-end leg")
+    ap.add_argument("--callers", type=int, default=2, help="concurrent host callers in the flat end-to-end leg")
+    ap.add_argument("--pgp-callers", type=int, default=2, help="concurrent host callers in the packet-level end-to-end leg")
     ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -15,7 +15,8 @@ class BftqError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [("items", C.c_uint64), ("launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("packer_chunks", C.c_uint64),
+                ("packer_parse_ns", C.c_uint64), ("packer_stage_ns", C.c_uint64), ("packer_wait_ns", C.c_uint64)]
 
 
 _lib = None

@@ -15,12 +15,15 @@
 #include "wotqs_host.hpp"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
 #include <tuple>
 #include <memory>
@@ -102,6 +105,66 @@ struct StagingSlot {
 
 }  // namespace
 
+// Persistent host workers for the packet-level entry points.  A batch call posts a job (its worker body) and
+// works on it itself; idle pool threads join the oldest job that still has chunks to hand out.  Threads are
+// created once (spawning 16 threads per call cost 0.5 ms of a 2.6 ms batch) and keep their per-thread caches.
+struct PackerPool {
+  struct Job {
+    std::function<void()> body;
+    std::function<bool()> has_work;          // false once every chunk has been handed out
+    unsigned max_joiners = 0, joined = 0;    // pool threads allowed to / that did join (under PackerPool::mu)
+    unsigned active = 0;                     // pool threads currently inside body()
+  };
+  std::mutex mu;
+  std::condition_variable cv_jobs, cv_idle;
+  std::deque<std::shared_ptr<Job>> jobs;
+  std::vector<std::thread> threads;
+  bool stop = false;
+
+  void ensure(unsigned n) {                  // grow to n threads (under mu)
+    while (threads.size() < n) threads.emplace_back([this] { loop(); });
+  }
+  void loop() {
+    std::unique_lock<std::mutex> l(mu);
+    for (;;) {
+      std::shared_ptr<Job> j;
+      cv_jobs.wait(l, [&] {
+        if (stop) return true;
+        for (auto& c : jobs) if (c->joined < c->max_joiners && c->has_work()) { j = c; return true; }
+        return false;
+      });
+      if (stop) return;
+      j->joined++; j->active++;
+      l.unlock();
+      j->body();
+      l.lock();
+      j->active--;
+      cv_idle.notify_all();
+    }
+  }
+  // Runs body on the calling thread and on up to `helpers` pool threads; returns when all of them are out.
+  void run(unsigned helpers, std::function<void()> body, std::function<bool()> has_work) {
+    auto j = std::make_shared<Job>();
+    j->body = body; j->has_work = std::move(has_work); j->max_joiners = helpers;
+    if (helpers) {
+      std::lock_guard<std::mutex> l(mu);
+      ensure(helpers);
+      jobs.push_back(j);
+    }
+    if (helpers) cv_jobs.notify_all();
+    body();
+    if (!helpers) return;
+    std::unique_lock<std::mutex> l(mu);
+    for (auto it = jobs.begin(); it != jobs.end(); ++it) if (*it == j) { jobs.erase(it); break; }
+    cv_idle.wait(l, [&] { return j->active == 0; });
+  }
+  ~PackerPool() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv_jobs.notify_all();
+    for (auto& t : threads) t.join();
+  }
+};
+
 struct bftq_engine {
   int device = 0;
   int sm_count = 0;
@@ -119,7 +182,7 @@ struct bftq_engine {
   struct DsaKey { std::vector<uint8_t> p, q, gy; int cls; };   // gy: g || y, each padded to |p| bytes
   std::vector<DsaKey> dsa_keys;                  // host table; a group's domain travels with its launch
   std::map<std::string, uint32_t> dsa_lookup;
-  std::atomic<int> packer_workers{0};            // packer worker threads alive across all concurrent batch calls
+  PackerPool pool;                               // host workers of the packet-level entry points
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
@@ -438,8 +501,9 @@ int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t strid
     from_be(n, n_be + (size_t)k * stride, stride);
     const int nb = bitlen(n);
     const int kb = (nb + 7) / 8;
-    if (!bftq::class_supported(kb) || !(n.w[0] & 1))
-      return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd with ceil(bits/8) in {128,192,256,384,512} (key " + std::to_string(k) + ")");
+    const int cls = bftq::class_of(kb);
+    if (!cls || !(n.w[0] & 1))
+      return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd and at most 4096 bits (key " + std::to_string(k) + ")");
     if (exps[k] == 0) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "public exponent 0");
     bftq::RsaKeyDev& kd = fresh[k];
     memset(&kd, 0, sizeof(kd));
@@ -457,7 +521,7 @@ int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t strid
     x.w[0] = 1;
     int exp2 = 0;
     for (int layout = 0; layout < bftq::kNumLayouts; layout++) {
-      const int digits = bftq::class_digits(kb, layout == 1 && kb != 256 ? 0 : layout);
+      const int digits = bftq::class_digits(cls, layout == 1 && cls != 256 ? 0 : layout);
       const int target = 2 * 28 * digits;
       while (exp2 < target) { dbl_mod(x, n); exp2++; }
       if (exp2 == target) to_digits(x, kd.r2[layout], bftq::kMaxDigits);
@@ -476,7 +540,7 @@ int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t strid
       for (int ex = 0; ex < 4096; ex++) dbl_mod(y, n);
       for (int i = 0; i < 32; i++) { k32.r2[2 * i] = (uint32_t)y.w[i]; k32.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
     }
-    if (kb == 256 && nb != 2048) fresh_all_2048 = false;
+    if (cls == 256 && nb != 2048) fresh_all_2048 = false;
   }
   std::lock_guard<std::mutex> g(e->mu);
   CU(cudaSetDevice(e->device));
@@ -1215,7 +1279,7 @@ namespace pg = bftq::pgp;
 int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
   if (!e) return -1;
   if (!(k.algo == 1 || k.algo == 2 || k.algo == 3)) return -1;
-  if (!bftq::class_supported((int)(k.nbits + 7) / 8) || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
+  if (!bftq::class_of((int)(k.nbits + 7) / 8) || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
   std::string id((const char*)k.n_be.data(), k.n_be.size());
   id.append((const char*)&k.e, 4);
   {
@@ -1348,12 +1412,15 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
         if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
         if (t.key_idx < 0) t.key_idx = 0;
         t.alg = 1; t.kbytes = 0;
+        size_t key_len = 0;
         const bool ec = sp.pk_algo == 19 && kr.key->algo == 19, dsa = sp.pk_algo == 17 && kr.key->algo == 17;
         if (ec) t.alg = 19;
         else if (dsa) { t.alg = 17; t.kbytes = (uint32_t)t.key_idx; }
         else {
-          const size_t kb = (kr.key->nbits + 7) / 8;                                  // pub.Size()
-          t.kbytes = (uint32_t)(bftq::class_supported((int)kb) ? kb : 256);
+          key_len = (kr.key->nbits + 7) / 8;                                          // pub.Size()
+          const int cls = bftq::class_of((int)key_len);
+          t.kbytes = (uint32_t)(cls ? cls : 256);                                     // travels in its size class
+          if (!cls) key_len = 256;
         }
         const uint32_t nb = sig_bytes_of(t.alg, t.kbytes);
         t.sig_pos = (uint32_t)pl.sig_blob.size();
@@ -1367,7 +1434,7 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
           }
           if (ec && kr.key->ec_xy.size() == 64) memcpy(dst + 64, kr.key->ec_xy.data(), 64);
         } else {
-          if (sp.mpi.size() <= t.kbytes) { if (sp.mpi.size()) memcpy(dst + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size()); }   // padToKeySize
+          if (sp.mpi.size() <= key_len) { if (sp.mpi.size()) memcpy(dst + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size()); }   // padToKeySize
           else if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE;                             // len(sig) != k
         }
         pl.tuples.push_back(t);
@@ -1572,26 +1639,19 @@ uint64_t packer_chunk() {
 // into the caller's outputs (disjoint item ranges, so no locking).  e == nullptr: parse only.
 template <typename Build, typename Done>
 int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build build, Done done) {
-  unsigned want = max_threads ? max_threads : packer_threads();
-  // Concurrent batch calls share the host: a call starts only as many workers as the budget has left
-  // (at least one), so four callers do not put 64 threads on 16 cores.
-  int taken = 0;
-  if (e && !max_threads) {
-    const int budget = (int)want;
-    int cur = e->packer_workers.load();
-    for (;;) {
-      taken = std::max(1, budget - cur);
-      if (e->packer_workers.compare_exchange_weak(cur, cur + taken)) break;
-    }
-    want = (unsigned)taken;
-  }
+  const unsigned want = max_threads ? max_threads : packer_threads();
   // Chunk size: small enough that every worker gets several chunks (so its parsing overlaps the kernels
   // of its previous chunks and the GPU starts early), large enough to amortise the per-chunk driver calls.
   uint64_t chunk = packer_chunk();
   if (!chunk) chunk = std::min<uint64_t>(4096, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * 4) + 63) / 64) * 64));
   const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
   const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, n_chunks));
-  const bool sleepy = [] { const char* v = getenv("BFTQ_SPIN_SYNC"); return !(v && atoi(v) > 0); }();
+  // Waiting for a chunk: spinning in cudaStreamSynchronize measured 31 M/s against 24 M/s with a blocking-sync
+  // event (tools/pgp_e2e_experiment.py) — the wake-up latency costs more than the spinning; BFTQ_BLOCKING_SYNC=1
+  // selects the sleeping wait for hosts where the CPU quota is the scarcer resource.
+  const bool sleepy = [] { const char* v = getenv("BFTQ_BLOCKING_SYNC"); return v && atoi(v) > 0; }();
+  const bool tracing = getenv("BFTQ_TRACE") != nullptr;
+  const auto call_t0 = std::chrono::steady_clock::now();
   std::atomic<uint64_t> next{0};
   std::atomic<int> first_err{BFTQ_OK};
   std::mutex err_mu;
@@ -1606,9 +1666,18 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
       std::lock_guard<std::mutex> lk(err_mu);
       if (first_err.load() == BFTQ_OK) { first_err.store(rc); err_text = g_last_error; }
     };
+    uint64_t parse_ns = 0, stage_ns = 0, wait_ns = 0, chunks = 0;
+    std::vector<std::array<double, 6>> trace;     // BFTQ_TRACE: per chunk (index, parse start, parse end, enqueue end, wait start, wait end) in us
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count();
+    };
     auto retire = [&]() {
       PlanRun& pv = runs[tail % kDepth];
+      const auto t0 = now();
       if (e) note(plan_finish(pv));
+      wait_ns += ns(t0, now());
+      if (tracing) for (auto& tr : trace) if ((uint64_t)tr[0] == pv.lo / chunk) { tr[4] = ns(call_t0, t0) * 1e-3; tr[5] = ns(call_t0, now()) * 1e-3; }
       if (first_err.load() == BFTQ_OK) done(pv);
       tail++;
     };
@@ -1619,20 +1688,37 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
       PlanRun& pr = runs[head % kDepth];
       pr.lo = c * chunk; pr.hi = std::min(n_items, pr.lo + chunk);
       pr.pl.reset();
+      const auto t0 = now();
       build(pr.lo, pr.hi, pr.pl);
+      const auto t1 = now();
       if (e) note(plan_enqueue(e, pr, sleepy)); else split_groups(pr);
+      parse_ns += ns(t0, t1); stage_ns += ns(t1, now()); chunks++;
+      if (tracing) trace.push_back({(double)c, ns(call_t0, t0) * 1e-3, ns(call_t0, t1) * 1e-3, ns(call_t0, now()) * 1e-3, 0.0, 0.0});
       head++;
     }
     while (tail < head) retire();
+    if (tracing) {
+      std::lock_guard<std::mutex> lk(err_mu);
+      for (auto& tr : trace)
+        fprintf(stderr, "bftq-trace chunk %4d thread %zu parse %8.1f..%8.1f enqueued %8.1f wait %8.1f..%8.1f us\n", (int)tr[0],
+                std::hash<std::thread::id>()(std::this_thread::get_id()) % 1000, tr[1], tr[2], tr[3], tr[4], tr[5]);
+    }
+    if (e) {
+      std::lock_guard<std::mutex> lk(e->mu);
+      e->stats.packer_chunks += chunks; e->stats.packer_parse_ns += parse_ns; e->stats.packer_stage_ns += stage_ns; e->stats.packer_wait_ns += wait_ns;
+    }
     for (auto& r : runs) for (auto& g : r.groups) if (g.arena) g.arena->finish();      // error path: let in-flight copies land
   };
+  // The caller works too; nthreads - 1 helpers come from the engine's pool (concurrent calls share its threads,
+  // oldest job first).  Without an engine (parse-only diagnostics) plain threads do.
   if (nthreads <= 1) worker();
+  else if (e) e->pool.run(nthreads - 1, worker, [&] { return next.load() < n_chunks; });
   else {
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (unsigned t = 0; t + 1 < nthreads; t++) th.emplace_back(worker);
+    worker();
     for (auto& t : th) t.join();
   }
-  if (taken) e->packer_workers.fetch_sub(taken);
   if (first_err.load() != BFTQ_OK) return fail(first_err.load(), err_text);
   return BFTQ_OK;
 }

@@ -39,6 +39,10 @@ __host__ __device__ constexpr int class_digits(int kb, int layout) {
   return kb == 128 ? 40 : kb == 192 ? 56 : kb == 256 ? (layout == 0 ? 76 : 80) : kb == 384 ? 112 : kb == 512 ? 152 : 0;
 }
 __host__ inline bool class_supported(int kb) { return kb == 128 || kb == 192 || kb == 256 || kb == 384 || kb == 512; }
+// Key-size class that carries a modulus of kb = ceil(bits / 8) bytes: the smallest built class that holds it
+// (0: larger than any).  A 2056-bit key (k = 257) runs in the 384-byte class: its signatures are left-padded to
+// the class stride, the arithmetic is the same Montgomery product with a larger R, and EM is built for k = 257.
+__host__ __device__ constexpr int class_of(int kb) { return kb < 1 ? 0 : kb <= 128 ? 128 : kb <= 192 ? 192 : kb <= 256 ? 256 : kb <= 384 ? 384 : kb <= 512 ? 512 : 0; }
 
 // Per-key constants, precomputed on the host at bftq_register_rsa_keys().
 struct RsaKeyDev {
@@ -47,7 +51,7 @@ struct RsaKeyDev {
   uint32_t n0inv;                         // -n^-1 mod 2^28
   uint32_t e;                             // public exponent (>= 1)
   uint32_t nbits;
-  uint32_t kbytes;                        // key-size class = ceil(nbits / 8)
+  uint32_t kbytes;                        // k = ceil(nbits / 8) = pub.Size(): the length of EM and of a signature
 };
 
 // DigestInfo prefixes, identical to Go's crypto/rsa hashPrefixes (and to the copy in the
@@ -102,6 +106,29 @@ __device__ __forceinline__ uint32_t em_word(int k, const uint8_t* digest, int pl
   const int b = (KB - 4) - 4 * k;
   return (em_byte<KB>(b, digest, plen, dlen, hash_alg) << 24) | (em_byte<KB>(b + 1, digest, plen, dlen, hash_alg) << 16) |
          (em_byte<KB>(b + 2, digest, plen, dlen, hash_alg) << 8) | em_byte<KB>(b + 3, digest, plen, dlen, hash_alg);
+}
+
+// The same with the key's own length k (bytes) at run time, for the size-class kernels: byte i of the k-byte EM,
+// and the 32-bit little-endian word w of EM read as a number (zero above k bytes).
+__device__ __forceinline__ uint32_t em_byte_k(int i, int k, const uint8_t* digest, int plen, int dlen, uint32_t hash_alg) {
+  const int t0 = k - (plen + dlen);
+  if (i >= t0) {
+    const int t = i - t0;
+    return t < plen ? (uint32_t)c_hash_prefix[hash_alg].bytes[t] : (uint32_t)__ldg(digest + (t - plen));
+  }
+  if (i == 0) return 0u;
+  if (i == 1) return 1u;
+  if (i == t0 - 1) return 0u;
+  return 0xFFu;
+}
+__device__ __forceinline__ uint32_t em_word_k(int w, int k, const uint8_t* digest, int plen, int dlen, uint32_t hash_alg) {
+  uint32_t v = 0u;
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int j = 4 * w + t;                       // byte offset from the least significant end
+    if (j < k) v |= em_byte_k(k - 1 - j, k, digest, plen, dlen, hash_alg) << (8 * t);
+  }
+  return v;
 }
 
 // ---- Montgomery product, radix 2^28, T lanes x W digits ---------------------------------------
@@ -204,7 +231,11 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     const bool known = kidx < nkeys;
     if (!known) kidx = 0u;
     const RsaKeyDev* __restrict__ key = keys + kidx;
-    const bool wrong_class = __ldg(&key->kbytes) != (uint32_t)KB;    // len(sig) != k: rsa.VerifyPKCS1v15 fails
+    // k = pub.Size().  rsa.VerifyPKCS1v15: "if k < tLen+11 return ErrVerification" and "k != len(sig)" — the
+    // signature travels left-padded to the class stride KB >= k, so a non-zero byte above its low k bytes means
+    // the caller's signature was longer than k.
+    const int kk = (int)__ldg(&key->kbytes);
+    bool wrong_class = class_of(kk) != KB || kk < plen + dlen + 11;     // (a key of another class has the wrong R^2)
 
     uint32_t nd[W], xs[W], xm[W], y[W];
 #pragma unroll
@@ -214,6 +245,11 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
 
     // s -> radix 2^28 digits (canonical).
     const uint8_t* sp = sig + item * (uint64_t)KB;
+    if (kk < KB) {
+      bool longer = false;
+      for (int i = r; i < KB - kk; i += T) longer = longer || (__ldg(sp + i) != 0);
+      wrong_class = wrong_class || ((__ballot_sync(kFull, longer) >> gbase) & ((T == 32) ? 0xffffffffu : ((1u << T) - 1u))) != 0u;
+    }
 #pragma unroll
     for (int j = 0; j < W; j++) {
       const int o = kDigitBits * (r * W + j);
@@ -286,16 +322,16 @@ rsa_verify_kernel(const RsaKeyDev* __restrict__ keys, const uint32_t nkeys, cons
     }
     canonicalise<T, W>(y, r);
 
-    // Compare with the expected encoded message.  y < n(1 + 2^-24) and EM < n, and y == EM + n is
-    // impossible for a 2041..2048-bit modulus, so a canonical digit compare decides.
+    // Compare with the expected encoded message.  y < n(1 + 2^-24), and y == EM + n would need EM < 2^-24 n while
+    // EM = 00 01 FF.. is at least 2^-16 n for a modulus of k bytes, so a canonical digit compare decides.
     const uint8_t* dp = digest + item * (uint64_t)dlen;
     bool eq = true;
 #pragma unroll
     for (int j = 0; j < W; j++) {
       const int o = kDigitBits * (r * W + j);
       const int wi = o >> 5, sh = o & 31;
-      const uint32_t lo = em_word<KB>(wi, dp, plen, dlen, hash_alg);
-      const uint32_t hi = em_word<KB>(wi + 1, dp, plen, dlen, hash_alg);
+      const uint32_t lo = em_word_k(wi, kk, dp, plen, dlen, hash_alg);
+      const uint32_t hi = em_word_k(wi + 1, kk, dp, plen, dlen, hash_alg);
       const uint32_t emd = __funnelshift_r(lo, hi, sh) & kDigitMask;
       eq = eq && (emd == y[j]);
     }

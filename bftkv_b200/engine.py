@@ -264,7 +264,9 @@ class Engine:
     def stats(self):
         s = _lib.Stats()
         _lib.check(self._lib.bftq_stats(self._h, C.byref(s)))
-        return {"items": s.items, "launches": s.launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+        return {"items": s.items, "launches": s.launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes,
+                "packer_chunks": s.packer_chunks, "packer_parse_ns": s.packer_parse_ns, "packer_stage_ns": s.packer_stage_ns,
+                "packer_wait_ns": s.packer_wait_ns}
 
     def measure_int_peak(self) -> float:
         v = C.c_double()

@@ -85,10 +85,10 @@ int  bftq_device_sm_count(bftq_engine* e);
  * reached from crypto/pgp/crypto_pgp.go:324,338,490.  Registers `count` RSA public keys:
  * n_be = count x 256 bytes (big-endian modulus, left-padded), e = count public exponents.
  * Precomputes the per-key Montgomery constants once.  Keys are appended; *first_index receives
- * the index of the first new key (indices are what key_idx[] refers to).  A key's size class is
- * k = ceil(bits/8) (Go's pub.Size()); classes built: 128, 192, 256, 384, 512 bytes (RSA-1024 ...
- * RSA-4096).  Exactly-2048-bit moduli (what gpg --quick-gen-key rsa2048 produces) take the
- * radix-2^32 fast path. */
+ * the index of the first new key (indices are what key_idx[] refers to).  Any odd modulus of up to
+ * 4096 bits is accepted; a key of k = ceil(bits/8) bytes (Go's pub.Size()) travels in the smallest
+ * size class that holds it — 128, 192, 256, 384 or 512 bytes — and its EM is built for its own k.
+ * Exactly-2048-bit moduli (what gpg --quick-gen-key rsa2048 produces) take the radix-2^32 fast path. */
 int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* exps,
                            uint32_t count, uint32_t* first_index);
 /* Same with moduli of up to 512 bytes: n_be = count x stride bytes, each left-padded. */
@@ -117,8 +117,9 @@ int bftq_rsa_verify_batch_dev(bftq_engine* e, const uint32_t* d_key_idx, const u
                               const uint8_t* d_digest, uint32_t hash_alg, uint64_t n_items,
                               uint32_t flags, uint8_t* d_status, void* cuda_stream);
 
-/* Key-size-class forms: every signature of the batch is key_bytes long (128/192/256/384/512) and
- * must refer to keys of that class — a key of another class gives BFTQ_ST_BAD_SIGNATURE, as
+/* Key-size-class forms: every signature of the batch is stored in key_bytes bytes (128/192/256/384/512),
+ * left-padded, and must refer to keys of that class (k <= key_bytes, no smaller class holds k).  A key of
+ * another class, or non-zero bytes above the key's own k, give BFTQ_ST_BAD_SIGNATURE, as
  * rsa.VerifyPKCS1v15 rejects len(sig) != k. */
 int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* key_idx, const uint8_t* sig_be,
                             const uint8_t* digest, uint32_t hash_alg, uint64_t n_items, uint32_t flags,
@@ -389,6 +390,11 @@ typedef struct {
   uint64_t launches;       /* CUDA kernel launches issued by this engine              */
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
+  /* host half of the packet-level entry points, summed over their worker threads (nanoseconds) */
+  uint64_t packer_chunks;    /* plans (chunks of a batch call) sent to the device                     */
+  uint64_t packer_parse_ns;  /* OpenPGP parsing + keyring lookup + tuple composition                  */
+  uint64_t packer_stage_ns;  /* composing the flat inputs in pinned staging + enqueueing copies/kernels */
+  uint64_t packer_wait_ns;   /* waiting for a chunk's results                                          */
 } bftq_stats_t;
 int bftq_stats(bftq_engine* e, bftq_stats_t* out);
 

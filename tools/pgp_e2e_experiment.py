@@ -52,17 +52,15 @@ def main():
         rows.append({"chunk": chunk, "threads": threads, "callers": callers, "verifies_per_sec": N * steps / dt, "ms_per_batch": dt / steps * 1e3})
         print(rows[-1], file=sys.stderr)
 
-    for spin in ("0", "1"):
-        os.environ["BFTQ_SPIN_SYNC"] = spin
-        for chunk in (0, 512, 1024, 2048, 4096):
-            run(chunk, 16, 1)
-            rows[-1]["spin"] = spin
-        for threads in (4, 8, 12, 16, 24):
-            run(0, threads, 1)
-            rows[-1]["spin"] = spin
-        for callers in (2, 4):
-            run(0, 16, callers)
-            rows[-1]["spin"] = spin
+    for chunk in (0, 512, 1024, 2048):
+        run(chunk, 16, 1)
+    for threads in (8, 12, 16, 20):
+        run(0, threads, 1)
+    for callers in (2, 3, 4):
+        run(0, 16, callers)
+    os.environ["BFTQ_BLOCKING_SYNC"] = "1"
+    run(0, 16, 1)
+    run(0, 16, 2)
     print(json.dumps(rows))
 
 
