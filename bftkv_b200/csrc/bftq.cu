@@ -11,6 +11,7 @@
 #include "p256.cuh"
 #include "dsa_verify.cuh"
 #include "pgp_digest.cuh"
+#include "pgp_parse.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
 
@@ -1387,8 +1388,8 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
       sp.write_suffix(pl.suffix_blob.data() + spos);
       uint32_t didx = data_plain;
       uint8_t common_pre = 0;
-      if (sp.version != 4) common_pre = BFTQ_ST_UNSUPPORTED;                    // SignatureV3: not built
-      else if (sp.sig_type == 0x01) {
+      // v4 and v3 (packet.SignatureV3 -> VerifySignatureV3: same digest rule, the suffix is sig type + creation time)
+      if (sp.sig_type == 0x01) {
         if (data_text < 0) {
           std::vector<uint8_t> t;
           canonical_text(tbs, tbs_len, t);
@@ -1399,7 +1400,7 @@ void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, cons
         didx = (uint32_t)data_text;
       } else if (sp.sig_type != 0x00) common_pre = BFTQ_ST_BAD_SIGNATURE;       // hashForSignature: unsupported type
       if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3 || sp.pk_algo == 17 || sp.pk_algo == 19)) common_pre = BFTQ_ST_UNSUPPORTED;
-      if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // MD5 / RIPEMD-160: not built
+      if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // RIPEMD-160: crypto.RIPEMD160 is not linked into bftkv -> "hash function unavailable"
       for (const pg::KeyRef& kr : keys) {
         Tuple t;
         t.item = item; t.call = calls; t.signer_id = kr.entity->primary.key_id;
@@ -1632,24 +1633,23 @@ uint64_t packer_chunk() {
   return 0;                 // 0: sized per call (run_batch)
 }
 
-// The packer's batch driver.  The batch is cut into chunks of packer_chunk() items; worker threads take
-// chunks off a shared counter, and each keeps two plans going: while the kernels of chunk c run on its
-// stream the thread parses chunk c+1, so packet parsing (CPU) and digest + verify (GPU) overlap both
-// across and inside threads.  build(lo, hi, plan) parses the items, done(planrun) folds the statuses
-// into the caller's outputs (disjoint item ranges, so no locking).  e == nullptr: parse only.
-template <typename Build, typename Done>
-int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build build, Done done) {
+// The packer's batch driver.  The batch is cut into chunks; worker threads (the caller plus helpers from the
+// engine's pool) take chunks off a shared counter, and each keeps kDepth runs in flight: while the kernels of
+// its earlier chunks run on their streams the thread prepares the next one, so host work (CPU) and digest +
+// verify (GPU) overlap both across and inside threads.
+//   submit(run, lo, hi, parse_ns)  prepares items [lo, hi) and enqueues their device work (no waiting)
+//   retire(run)                    waits for the run's results and folds them into the caller's outputs
+//                                  (disjoint item ranges, so no locking)
+//   drain(run)                     error path: lets the run's in-flight copies land
+template <typename RunT, typename Submit, typename Retire, typename Drain>
+int run_chunks(bftq_engine* e, uint64_t n_items, unsigned max_threads, uint64_t default_chunk_cap, Submit submit, Retire retire_fn, Drain drain) {
   const unsigned want = max_threads ? max_threads : packer_threads();
-  // Chunk size: small enough that every worker gets several chunks (so its parsing overlaps the kernels
+  // Chunk size: small enough that every worker gets several chunks (so its preparation overlaps the kernels
   // of its previous chunks and the GPU starts early), large enough to amortise the per-chunk driver calls.
   uint64_t chunk = packer_chunk();
-  if (!chunk) chunk = std::min<uint64_t>(4096, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * 4) + 63) / 64) * 64));
+  if (!chunk) chunk = std::min<uint64_t>(default_chunk_cap, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * 4) + 63) / 64) * 64));
   const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
   const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, n_chunks));
-  // Waiting for a chunk: spinning in cudaStreamSynchronize measured 31 M/s against 24 M/s with a blocking-sync
-  // event (tools/pgp_e2e_experiment.py) — the wake-up latency costs more than the spinning; BFTQ_BLOCKING_SYNC=1
-  // selects the sleeping wait for hosts where the CPU quota is the scarcer resource.
-  const bool sleepy = [] { const char* v = getenv("BFTQ_BLOCKING_SYNC"); return v && atoi(v) > 0; }();
   const bool tracing = getenv("BFTQ_TRACE") != nullptr;
   const auto call_t0 = std::chrono::steady_clock::now();
   std::atomic<uint64_t> next{0};
@@ -1658,8 +1658,9 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
   std::string err_text;
   auto worker = [&]() {
     if (e) cudaSetDevice(e->device);
-    constexpr int kDepth = 4;                    // plans a worker keeps in flight
-    PlanRun runs[kDepth];
+    constexpr int kDepth = 4;                    // runs a worker keeps in flight
+    RunT runs[kDepth];
+    uint64_t run_chunk[kDepth] = {0, 0, 0, 0};
     uint64_t head = 0, tail = 0;                 // runs[tail % kDepth .. head % kDepth) are in flight
     auto note = [&](int rc) {
       if (!rc) return;
@@ -1667,33 +1668,32 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
       if (first_err.load() == BFTQ_OK) { first_err.store(rc); err_text = g_last_error; }
     };
     uint64_t parse_ns = 0, stage_ns = 0, wait_ns = 0, chunks = 0;
-    std::vector<std::array<double, 6>> trace;     // BFTQ_TRACE: per chunk (index, parse start, parse end, enqueue end, wait start, wait end) in us
+    std::vector<std::array<double, 6>> trace;     // BFTQ_TRACE: per chunk (index, start, parsed, enqueued, wait start, wait end) in us
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
       return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count();
     };
     auto retire = [&]() {
-      PlanRun& pv = runs[tail % kDepth];
+      RunT& pv = runs[tail % kDepth];
       const auto t0 = now();
-      if (e) note(plan_finish(pv));
-      wait_ns += ns(t0, now());
-      if (tracing) for (auto& tr : trace) if ((uint64_t)tr[0] == pv.lo / chunk) { tr[4] = ns(call_t0, t0) * 1e-3; tr[5] = ns(call_t0, now()) * 1e-3; }
-      if (first_err.load() == BFTQ_OK) done(pv);
+      uint64_t w = 0;
+      if (first_err.load() == BFTQ_OK) note(retire_fn(pv, w)); else drain(pv);
+      wait_ns += w;
+      if (tracing) for (auto& tr : trace) if ((uint64_t)tr[0] == run_chunk[tail % kDepth]) { tr[4] = ns(call_t0, t0) * 1e-3; tr[5] = tr[4] + w * 1e-3; }
       tail++;
     };
     for (;;) {
       const uint64_t c = next.fetch_add(1);
       if (c >= n_chunks || first_err.load() != BFTQ_OK) break;
       if (head - tail == kDepth) retire();
-      PlanRun& pr = runs[head % kDepth];
-      pr.lo = c * chunk; pr.hi = std::min(n_items, pr.lo + chunk);
-      pr.pl.reset();
+      RunT& pr = runs[head % kDepth];
+      run_chunk[head % kDepth] = c;
       const auto t0 = now();
-      build(pr.lo, pr.hi, pr.pl);
-      const auto t1 = now();
-      if (e) note(plan_enqueue(e, pr, sleepy)); else split_groups(pr);
-      parse_ns += ns(t0, t1); stage_ns += ns(t1, now()); chunks++;
-      if (tracing) trace.push_back({(double)c, ns(call_t0, t0) * 1e-3, ns(call_t0, t1) * 1e-3, ns(call_t0, now()) * 1e-3, 0.0, 0.0});
+      uint64_t p_ns = 0;
+      note(submit(pr, c * chunk, std::min(n_items, c * chunk + chunk), p_ns));
+      const uint64_t total = ns(t0, now());
+      parse_ns += p_ns; stage_ns += total > p_ns ? total - p_ns : 0; chunks++;
+      if (tracing) trace.push_back({(double)c, ns(call_t0, t0) * 1e-3, (ns(call_t0, t0) + p_ns) * 1e-3, ns(call_t0, now()) * 1e-3, 0.0, 0.0});
       head++;
     }
     while (tail < head) retire();
@@ -1707,7 +1707,6 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
       std::lock_guard<std::mutex> lk(e->mu);
       e->stats.packer_chunks += chunks; e->stats.packer_parse_ns += parse_ns; e->stats.packer_stage_ns += stage_ns; e->stats.packer_wait_ns += wait_ns;
     }
-    for (auto& r : runs) for (auto& g : r.groups) if (g.arena) g.arena->finish();      // error path: let in-flight copies land
   };
   // The caller works too; nthreads - 1 helpers come from the engine's pool (concurrent calls share its threads,
   // oldest job first).  Without an engine (parse-only diagnostics) plain threads do.
@@ -1721,6 +1720,39 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
   }
   if (first_err.load() != BFTQ_OK) return fail(first_err.load(), err_text);
   return BFTQ_OK;
+}
+
+// Host-packer form: build(lo, hi, plan) parses the items, done(planrun) folds the statuses.  e == nullptr: parse only.
+template <typename Build, typename Done>
+int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build build, Done done) {
+  // Waiting for a chunk: spinning in cudaStreamSynchronize measured 31 M/s against 24 M/s with a blocking-sync
+  // event (tools/pgp_e2e_experiment.py) — the wake-up latency costs more than the spinning; BFTQ_BLOCKING_SYNC=1
+  // selects the sleeping wait for hosts where the CPU quota is the scarcer resource.
+  const bool sleepy = [] { const char* v = getenv("BFTQ_BLOCKING_SYNC"); return v && atoi(v) > 0; }();
+  auto tick = [] { return std::chrono::steady_clock::now(); };
+  auto since = [](std::chrono::steady_clock::time_point a) {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count();
+  };
+  return run_chunks<PlanRun>(
+      e, n_items, max_threads, 4096,
+      [&](PlanRun& pr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
+        pr.lo = lo; pr.hi = hi;
+        pr.pl.reset();
+        const auto t0 = tick();
+        build(lo, hi, pr.pl);
+        parse_ns = since(t0);
+        if (e) return plan_enqueue(e, pr, sleepy);
+        split_groups(pr);
+        return (int)BFTQ_OK;
+      },
+      [&](PlanRun& pr, uint64_t& wait_ns) {
+        const auto t0 = tick();
+        const int rc = e ? plan_finish(pr) : (int)BFTQ_OK;
+        wait_ns = since(t0);
+        if (!rc) done(pr);
+        return rc;
+      },
+      [&](PlanRun& pr) { for (auto& g : pr.groups) if (g.arena) { g.arena->finish(); g.arena.reset(); } });
 }
 
 int check_blobs(const void* blob, const uint64_t* off, uint64_t n) {
@@ -1796,9 +1828,95 @@ int bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids
   return fail(BFTQ_ERR_INVALID_ARG, "key id not in keyring");
 }
 
+// ---- GPU-parsed fast path of Signature.Verify's batch form (K0, pgp_parse.cuh) -------------------------
+namespace {
+
+// EntityList.KeysByIdUsage(id, KeyFlagSign) for every key id of the keyring, flattened for the device: an id
+// with exactly one usable RSA key of the 2048-bit size class is decided on the GPU, any other id that has
+// candidates is left to the host packer, and an id that is not in the table has no candidates at all.
+std::vector<bftq::IssuerEntry> build_issuer_table(const std::vector<const std::vector<pg::Entity>*>& rings) {
+  std::vector<bftq::IssuerEntry> tab;
+  std::vector<pg::KeyRef> keys;
+  auto add = [&](uint64_t id) {
+    for (auto& en : tab) if (en.key_id == id) return;
+    pg::keys_by_id_usage(rings, id, pg::kKeyFlagSign, keys);
+    if (keys.empty()) return;
+    bftq::IssuerEntry en{};
+    en.key_id = id; en.kind = 1;
+    const pg::PubKey& k = *keys[0].key;
+    const int kb = (int)((k.nbits + 7) / 8);
+    if (keys.size() == 1 && (k.algo == 1 || k.algo == 2 || k.algo == 3) && k.table_idx >= 0 && bftq::class_of(kb) == 256) {
+      en.kind = 0; en.key_idx = (uint32_t)k.table_idx; en.kbytes = (uint16_t)kb; en.algo = k.algo;
+    }
+    tab.push_back(en);
+  };
+  for (auto* ring : rings)
+    for (const pg::Entity& e : *ring) {
+      add(e.primary.key_id);
+      for (const pg::Subkey& sk : e.subkeys) add(sk.key.key_id);
+    }
+  return tab;
+}
+
+struct FastRun {
+  std::unique_ptr<Arena> arena;
+  std::vector<uint8_t> st, where;
+  uint64_t lo = 0, hi = 0;
+};
+
+// Copies the chunk's raw bytes into staging and enqueues K0 (parse + digest) and K1 on the slot's stream.
+int fast_enqueue(bftq_engine* e, FastRun& fr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
+                 const uint64_t* sig_off, const std::vector<bftq::IssuerEntry>& table) {
+  const uint64_t lo = fr.lo, hi = fr.hi;
+  const size_t n = (size_t)(hi - lo);
+  const uint64_t t0 = tbs_off[lo], tb = tbs_off[hi] - t0, g0 = sig_off[lo], gb = sig_off[hi] - g0;
+  fr.arena.reset(new Arena(e));
+  fr.st.assign(n, 0); fr.where.assign(n, 0);
+  Arena& a = *fr.arena;
+  uint8_t *d_tbs, *d_sig, *h_tbs, *h_sig, *d_pad, *d_dig, *d_pre, *d_st, *d_where;
+  uint64_t *d_toff, *d_soff, *h_toff, *h_soff;
+  bftq::IssuerEntry *d_tab, *h_tab;
+  uint32_t* d_kidx;
+  a.stage(&d_tbs, &h_tbs, std::max<size_t>(tb, 1));
+  a.stage(&d_toff, &h_toff, n + 1);
+  a.stage(&d_sig, &h_sig, std::max<size_t>(gb, 1));
+  a.stage(&d_soff, &h_soff, n + 1);
+  a.stage(&d_tab, &h_tab, std::max<size_t>(table.size(), 1));
+  a.out(&d_kidx, (uint32_t*)nullptr, n, 0);                // device-only intermediates: K0 -> K1
+  a.out(&d_pad, (uint8_t*)nullptr, n * 256, 0);
+  a.out(&d_dig, (uint8_t*)nullptr, n * 32, 0);
+  a.out(&d_pre, (uint8_t*)nullptr, n, 0);
+  a.out(&d_st, fr.st.data(), n);
+  a.out(&d_where, fr.where.data(), n);
+  int rc = a.prepare();
+  if (rc) return rc;
+  if (tb) memcpy(h_tbs, tbs_blob + t0, tb);
+  if (gb) memcpy(h_sig, sig_blob + g0, gb);
+  for (size_t i = 0; i <= n; i++) { h_toff[i] = tbs_off[lo + i] - t0; h_soff[i] = sig_off[lo + i] - g0; }
+  if (!table.empty()) memcpy(h_tab, table.data(), table.size() * sizeof(bftq::IssuerEntry));
+  rc = a.upload();
+  if (rc) return rc;
+  const int block = 128;
+  bftq::pgp_parse_digest_kernel<<<(unsigned)((n + block - 1) / block), block, 0, a.stream()>>>(
+      d_tbs, d_toff, d_sig, d_soff, (uint32_t)n, d_tab, (uint32_t)table.size(), d_kidx, d_pad, d_dig, d_pre, d_where);
+  CU(cudaGetLastError());
+  { std::lock_guard<std::mutex> lk(e->mu); e->stats.launches += 1; }
+  rc = launch_rsa_any(e, d_kidx, d_pad, d_dig, 8, n, 0, d_pre, d_st, a.stream(), 256);
+  if (rc) return rc;
+  return a.download_async();
+}
+
+bool gpu_parse_enabled() {
+  const char* v = getenv("BFTQ_GPU_PARSE");
+  return !(v && atoi(v) == 0);
+}
+
+}  // namespace
+
 static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
                              const uint64_t* sig_off, const uint8_t* cert_blob, const uint64_t* cert_off, uint64_t n_items,
-                             int32_t* out_err, bool parse_only = false, unsigned threads = 0, uint64_t* n_tuples = nullptr) {
+                             int32_t* out_err, bool parse_only = false, unsigned threads = 0, uint64_t* n_tuples = nullptr,
+                             bool no_gpu_parse = false) {
   if (!kr || (!out_err && !parse_only)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (!kr->e && !parse_only) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
   if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(sig_blob, sig_off, n_items) || (cert_off && check_blobs(cert_blob, cert_off, n_items)))
@@ -1807,6 +1925,51 @@ static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const ui
   std::vector<pg::Entity> sec, pub;                         // snapshot: Register / Remove may run concurrently (crypto_pgp.go:142-177)
   if (!cert_off) { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
   const std::vector<const std::vector<pg::Entity>*> shared_rings = {&sec, &pub};
+  // Fast path: the packets are parsed and hashed on the GPU (K0) and only the items it flags come back to the
+  // host packer below.  Needs the RSA key table on the device; VerifyWithCertificate (a keyring per item) and
+  // the parse-only diagnostic always take the host packer.
+  if (!cert_off && !parse_only && !no_gpu_parse && gpu_parse_enabled() && kr->e->d_keys && n_items < 0xffffffffull) {
+    const std::vector<bftq::IssuerEntry> table = build_issuer_table(shared_rings);
+    std::mutex fb_mu;
+    std::vector<uint64_t> fallback;
+    int rc = run_chunks<FastRun>(
+        kr->e, n_items, threads, 2048,
+        [&](FastRun& fr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
+          fr.lo = lo; fr.hi = hi; parse_ns = 0;
+          return fast_enqueue(kr->e, fr, tbs_blob, tbs_off, sig_blob, sig_off, table);
+        },
+        [&](FastRun& fr, uint64_t& wait_ns) {
+          const auto t0 = std::chrono::steady_clock::now();
+          const int r = fr.arena->finish();
+          wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+          fr.arena.reset();
+          if (r) return r;
+          std::vector<uint64_t> mine;
+          for (uint64_t i = fr.lo; i < fr.hi; i++) {
+            if (fr.where[i - fr.lo] == bftq::kParseDecided) out_err[i] = fr.st[i - fr.lo] == 0 ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
+            else mine.push_back(i);
+          }
+          if (!mine.empty()) { std::lock_guard<std::mutex> lk(fb_mu); fallback.insert(fallback.end(), mine.begin(), mine.end()); }
+          return (int)BFTQ_OK;
+        },
+        [&](FastRun& fr) { if (fr.arena) { fr.arena->finish(); fr.arena.reset(); } });
+    if (rc) return rc;
+    if (n_tuples) *n_tuples = n_items - fallback.size();
+    if (fallback.empty()) return BFTQ_OK;
+    // the flagged items, in item order, through the host packer
+    std::sort(fallback.begin(), fallback.end());
+    std::vector<uint8_t> tb, sb;
+    std::vector<uint64_t> to{0}, so{0};
+    for (uint64_t i : fallback) {
+      tb.insert(tb.end(), tbs_blob + tbs_off[i], tbs_blob + tbs_off[i + 1]); to.push_back(tb.size());
+      sb.insert(sb.end(), sig_blob + sig_off[i], sig_blob + sig_off[i + 1]); so.push_back(sb.size());
+    }
+    std::vector<int32_t> err(fallback.size(), BFTQ_ERR_INVALID_SIGNATURE);
+    rc = verify_batch_impl(kr, tb.data(), to.data(), sb.data(), so.data(), nullptr, nullptr, fallback.size(), err.data(), false, threads, nullptr, true);
+    if (rc) return rc;
+    for (size_t j = 0; j < fallback.size(); j++) out_err[fallback[j]] = err[j];
+    return BFTQ_OK;
+  }
   std::atomic<uint64_t> tuples{0};
   auto build = [&](uint64_t lo, uint64_t hi, Plan& pl) {
     std::vector<pg::Entity> cert_ring;                      // VerifyWithCertificate: a one-entity ring per item

@@ -109,6 +109,39 @@ __device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
 }
 
+__constant__ uint32_t c_md5_k[64] = {
+  0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u, 0x698098d8u, 0x8b44f7afu, 0xffff5bb1u,
+  0x895cd7beu, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u, 0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau, 0xd62f105du, 0x02441453u,
+  0xd8a1e681u, 0xe7d3fbc8u, 0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au, 0xfffa3942u,
+  0x8771f681u, 0x6d9d6122u, 0xfde5380cu, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u, 0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u,
+  0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u, 0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du,
+  0x85845dd1u, 0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u};
+__constant__ uint8_t c_md5_s[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9, 14, 20,
+                                    4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+
+// MD5 (RFC 1321): x/crypto links crypto/md5 (v3 key fingerprints), so hash id 1 is "available" to
+// hashForSignature and a foreign MD5 signature is verified, not refused.
+__device__ __forceinline__ void md5_compress(uint32_t (&h)[4], const uint32_t (&w)[16]) {
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
+#pragma unroll 1
+  for (int i = 0; i < 64; i++) {
+    uint32_t f; int g;
+    if (i < 16) { f = (b & c) | (~b & d); g = i; }
+    else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+    else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+    else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+    uint32_t wg = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) wg = (k == g) ? w[k] : wg;       // register file, no local-memory indexing
+    const uint32_t tmp = d;
+    d = c; c = b;
+    const uint32_t x = a + f + c_md5_k[i] + wg;
+    b = b + __funnelshift_l(x, x, c_md5_s[i]);
+    a = tmp;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+}
+
 struct DigestSrc {
   const uint8_t* dp; const uint8_t* sp; uint64_t dlen, total;
   __device__ __forceinline__ uint32_t byte(uint64_t pos) const {
@@ -118,7 +151,7 @@ struct DigestSrc {
   }
 };
 
-// ALG = OpenPGP hash id: 2 SHA-1, 8 SHA-256, 9 SHA-384, 10 SHA-512, 11 SHA-224.  out stride = digest length.
+// ALG = OpenPGP hash id: 1 MD5, 2 SHA-1, 8 SHA-256, 9 SHA-384, 10 SHA-512, 11 SHA-224.  out stride = digest length.
 template <int ALG>
 __global__ void __launch_bounds__(128)
 pgp_digest_kernel(const uint8_t* __restrict__ data_blob, const uint64_t* __restrict__ data_off,
@@ -131,7 +164,7 @@ pgp_digest_kernel(const uint8_t* __restrict__ data_blob, const uint64_t* __restr
   const uint64_t d0 = __ldg(data_off + di), d1 = __ldg(data_off + di + 1);
   const uint64_t s0 = __ldg(suffix_off + item), s1 = __ldg(suffix_off + item + 1);
   DigestSrc src{data_blob + d0, suffix_blob + s0, d1 - d0, (d1 - d0) + (s1 - s0)};
-  constexpr int kOutLen = ALG == 2 ? 20 : ALG == 8 ? 32 : ALG == 9 ? 48 : ALG == 10 ? 64 : 28;
+  constexpr int kOutLen = ALG == 1 ? 16 : ALG == 2 ? 20 : ALG == 8 ? 32 : ALG == 9 ? 48 : ALG == 10 ? 64 : 28;
   uint8_t* o = out_digest + item * kOutLen;
   uint32_t first16;
   if constexpr (ALG == 9 || ALG == 10) {
@@ -156,6 +189,24 @@ pgp_digest_kernel(const uint8_t* __restrict__ data_blob, const uint64_t* __restr
     for (int i = 0; i < kOutLen / 8; i++)
       for (int b = 0; b < 8; b++) o[8 * i + b] = (uint8_t)(h[i] >> (56 - 8 * b));
     first16 = (uint32_t)(h[0] >> 48);
+  } else if constexpr (ALG == 1) {
+    uint32_t h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    const uint64_t nblocks = (src.total + 9 + 63) / 64;
+    for (uint64_t blk = 0; blk < nblocks; blk++) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) v |= src.byte(blk * 64 + 4 * i + b) << (8 * b);       // little-endian words
+        w[i] = v;
+      }
+      if (blk == nblocks - 1) { w[14] = (uint32_t)(src.total * 8); w[15] = (uint32_t)((src.total * 8) >> 32); }
+      md5_compress(h, w);
+    }
+    for (int i = 0; i < 4; i++)
+      for (int b = 0; b < 4; b++) o[4 * i + b] = (uint8_t)(h[i] >> (8 * b));
+    first16 = ((h[0] & 0xffu) << 8) | ((h[0] >> 8) & 0xffu);
   } else if constexpr (ALG == 2) {
     uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
     const uint64_t nblocks = (src.total + 9 + 63) / 64;
@@ -202,7 +253,7 @@ pgp_digest_kernel(const uint8_t* __restrict__ data_blob, const uint64_t* __restr
   }
 }
 
-inline bool digest_on_device(uint32_t hash_alg) { return hash_alg == 2 || hash_alg == 8 || hash_alg == 9 || hash_alg == 10 || hash_alg == 11; }
+inline bool digest_on_device(uint32_t hash_alg) { return hash_alg == 1 || hash_alg == 2 || hash_alg == 8 || hash_alg == 9 || hash_alg == 10 || hash_alg == 11; }
 
 inline cudaError_t launch_pgp_digest(uint32_t hash_alg, const uint8_t* data_blob, const uint64_t* data_off, const uint32_t* data_idx,
                                      const uint8_t* suffix_blob, const uint64_t* suffix_off, uint64_t n, uint8_t* out, const uint16_t* tags,
@@ -210,6 +261,7 @@ inline cudaError_t launch_pgp_digest(uint32_t hash_alg, const uint8_t* data_blob
   const int block = 128;
   const unsigned grid = (unsigned)((n + block - 1) / block);
   switch (hash_alg) {
+    case 1: pgp_digest_kernel<1><<<grid, block, 0, st>>>(data_blob, data_off, data_idx, suffix_blob, suffix_off, n, out, tags, pre); break;
     case 2: pgp_digest_kernel<2><<<grid, block, 0, st>>>(data_blob, data_off, data_idx, suffix_blob, suffix_off, n, out, tags, pre); break;
     case 8: pgp_digest_kernel<8><<<grid, block, 0, st>>>(data_blob, data_off, data_idx, suffix_blob, suffix_off, n, out, tags, pre); break;
     case 9: pgp_digest_kernel<9><<<grid, block, 0, st>>>(data_blob, data_off, data_idx, suffix_blob, suffix_off, n, out, tags, pre); break;

@@ -161,10 +161,15 @@ inline int parse_signature(const uint8_t* b, size_t n, SigPacket& s) {
     if (!hash_digest_len(s.hash_id)) return kUnsupported;
     s.hashed = Span{b + 2, 5};
     s.hash_tag[0] = b[17]; s.hash_tag[1] = b[18];
-    if (s.pk_algo == 1 || s.pk_algo == 3) {
-      size_t p = 19; const uint8_t* md; size_t ml; unsigned bits;
+    size_t p = 19; const uint8_t* md; size_t ml; unsigned bits;
+    if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
+    if (s.pk_algo == 1 || s.pk_algo == 3) s.mpi = Span{md, ml};
+    else {                                                         // DSA: r, s
+      while (ml && *md == 0) { md++; ml--; }
+      s.r = Span{md, ml};
       if (read_mpi(b, n, p, md, ml, bits)) return kStructural;
-      s.mpi = Span{md, ml};
+      while (ml && *md == 0) { md++; ml--; }
+      s.s = Span{md, ml};
     }
     return kOk;
   }

@@ -1,0 +1,102 @@
+// K0 — OpenPGP signature packets parsed ON THE GPU (fast path of the packer) fused with K4's digest.
+//
+// Signature.Verify's batch form (crypto/pgp/crypto_pgp.go:319-330) spends, per item, ~0.3 us of host CPU on
+// packet parsing, keyring lookup and tuple composition; at 47 M verifies/s that is 14 host cores.  Almost every
+// bftkv signature has one shape — SignaturePacket.Data is ONE definite-length v4 RSA/SHA-256 binary signature
+// packet whose issuer has exactly one usable key in the keyring — so this kernel takes the raw bytes as the caller
+// handed them over, and per item (one thread):
+//   1. parses the packet with pgp_fastparse.hpp (same rules as pgp_host.hpp, fuzzed against it on the host),
+//   2. looks the issuer up in the call's issuer table (EntityList.KeysByIdUsage(id, KeyFlagSign) precomputed
+//      per key id on the host: one usable RSA key of the 2048-bit class -> key index; anything else -> host),
+//   3. left-pads the signature MPI to the key size (x/crypto padToKeySize) into K1's input layout,
+//   4. hashes  signed bytes || hashed area || 04 FF len32  (SHA-256) and applies the 16-bit hash-tag check,
+// and leaves key index / padded signature / digest / pre-status exactly as the host packer would have composed
+// them, for K1.  Whatever is not that shape is flagged and goes through the host packer afterwards — a fallback
+// is always safe; the flag, not a guess, decides.  The host's share drops to copying the raw bytes into staging.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "pgp_digest.cuh"
+#include "pgp_fastparse.hpp"
+
+namespace bftq {
+
+struct IssuerEntry {
+  uint64_t key_id;
+  uint32_t key_idx;        // engine key table index (kind 0)
+  uint16_t kbytes;         // pub.Size() of that key
+  uint8_t algo;            // the key's public-key algorithm (1, 2 or 3)
+  uint8_t kind;            // 0: exactly one usable RSA key, size class 256 -> decide here; 1: leave to the host packer
+};
+
+constexpr uint8_t kParseDecided = 0, kParseHost = 1;
+
+// Bytes of  data || hashed || trailer(6)  as one stream, then SHA-256 padding.
+struct FastSrc {
+  const uint8_t* dp; const uint8_t* hp; uint32_t dlen, hlen, total;
+  __device__ __forceinline__ uint32_t byte(uint32_t pos) const {
+    if (pos < dlen) return __ldg(dp + pos);
+    uint32_t q = pos - dlen;
+    if (q < hlen) return __ldg(hp + q);
+    q -= hlen;
+    if (q < 6) return q == 0 ? 0x04u : q == 1 ? 0xffu : ((hlen >> (8 * (5 - q))) & 0xffu);
+    return pos == total ? 0x80u : 0u;
+  }
+};
+
+__global__ void __launch_bounds__(128)
+pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __restrict__ tbs_off,
+                        const uint8_t* __restrict__ sig_blob, const uint64_t* __restrict__ sig_off, const uint32_t n_items,
+                        const IssuerEntry* __restrict__ issuers, const uint32_t n_issuers,
+                        uint32_t* __restrict__ out_key_idx, uint8_t* __restrict__ out_sig /* n x 256 */,
+                        uint8_t* __restrict__ out_digest /* n x 32 */, uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const uint64_t s0 = tbs_off[item], s1 = tbs_off[item + 1], g0 = sig_off[item], g1 = sig_off[item + 1];
+  const uint8_t* sg = sig_blob + g0;
+  out_key_idx[item] = 0u;
+  auto to_host = [&]() { out_where[item] = kParseHost; out_pre[item] = 6; /* BFTQ_ST_MISSING: K1 leaves the item alone */ };
+  fastparse::FastSig f;
+  if (s1 - s0 > 0x3fffffffull || fastparse::parse(sg, (size_t)(g1 - g0), f) != fastparse::kFast) { to_host(); return; }
+  if (f.hash_id != 8 || f.sig_type != 0x00) { to_host(); return; }       // other digests / text mode: host packer (K4 has them all)
+  int hit = -1;
+  for (uint32_t i = 0; i < n_issuers; i++) if (issuers[i].key_id == f.issuer) { hit = (int)i; break; }
+  out_where[item] = kParseDecided;
+  if (hit < 0) { out_pre[item] = 4; return; }                              // BFTQ_ST_UNKNOWN_SIGNER: the stream ends -> ErrUnknownIssuer
+  const IssuerEntry en = issuers[hit];
+  if (en.kind != 0) { to_host(); return; }
+  out_key_idx[item] = en.key_idx;
+  uint8_t pre = 0;
+  if (en.algo != f.pk_algo) pre = 1;                                       // "public key and signature use different algorithms"
+  uint8_t* so = out_sig + (size_t)item * 256;
+  if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }                        // len(sig) != k
+  else {
+    const uint32_t padn = 256u - f.mpi_len;
+    for (uint32_t i = 0; i < padn; i++) so[i] = 0;
+    for (uint32_t i = 0; i < f.mpi_len; i++) so[padn + i] = sg[f.mpi_off + i];
+  }
+  // digest (K4's SHA-256 arm over three segments) + x/crypto's 16-bit quick check
+  FastSrc src{tbs_blob + s0, sg + f.hashed_off, (uint32_t)(s1 - s0), f.hashed_len, 0};
+  src.total = src.dlen + src.hlen + 6;
+  uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  const uint32_t nblocks = (src.total + 9 + 63) / 64;
+  for (uint32_t blk = 0; blk < nblocks; blk++) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) v = (v << 8) | src.byte(blk * 64 + 4 * i + b);
+      w[i] = v;
+    }
+    if (blk == nblocks - 1) { w[14] = 0u; w[15] = src.total * 8u; }
+    sha256_compress(h, w);
+  }
+  uint8_t* o = out_digest + (size_t)item * 32;
+  for (int i = 0; i < 8; i++)
+    for (int b = 0; b < 4; b++) o[4 * i + b] = (uint8_t)(h[i] >> (24 - 8 * b));
+  if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;                    // BFTQ_ST_HASH_TAG
+  out_pre[item] = pre;
+}
+
+}  // namespace bftq

@@ -336,6 +336,9 @@ def _parse_signature_v3(body: bytes) -> Signature:
     if sig.pk_algo in (1, 3):
         sig.rsa_sig, bits, q = read_mpi(body, 19)
         sig.rsa_sig_bytes = body[21:q]
+    else:                                           # SignatureV3.parse: DSASigR, DSASigS
+        sig.sig_r, bits, q = read_mpi(body, 19)
+        sig.sig_s, bits, q = read_mpi(body, q)
     return sig
 
 

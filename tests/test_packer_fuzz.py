@@ -137,3 +137,34 @@ def test_plan_measure_counts_tuples_like_the_oracle(built):
             del os.environ["BFTQ_PLAN_CHUNK"]
         assert nt.value == expect, (threads, chunk, nt.value, expect)
     kr.close()
+
+
+def test_gpu_fast_parser_agrees_with_host_parser(golden):
+    """K0's packet parser (bftkv_b200/csrc/pgp_fastparse.hpp, the same source the kernel compiles) built for
+    the host and fuzzed against pgp_host.hpp: over a million mutated / truncated / spliced streams, whenever
+    it answers "fast" the reference-shaped parser reads the same stream to the same fields (a "fallback"
+    answer is always allowed — those items go through the host packer)."""
+    import os
+    import struct
+    import subprocess
+    from bftkv_b200 import workload
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "harness", "fastparse_host")
+    src = os.path.join(root, "tests", "harness", "fastparse_host.cpp")
+    deps = [src] + [os.path.join(root, "bftkv_b200", "csrc", f) for f in ("pgp_fastparse.hpp", "pgp_host.hpp")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, src])
+    w = workload.make_pgp_verify_batch(48, n_keys=4)
+    seeds = list(w["sigs"]) + [bytes.fromhex(c["sig"]) for c in golden["cases"]]
+    for s in list(seeds[:8]):                                   # the same bodies under new-format headers
+        body = s[3:]
+        seeds.append(bytes([0xC2, 0xFF]) + struct.pack(">I", len(body)) + body)
+        seeds.append(bytes([0xC2, ((len(body) - 192) >> 8) + 192, (len(body) - 192) & 0xFF]) + body)
+    path = os.path.join(root, "tests", "harness", "fastparse_seeds.bin")
+    with open(path, "wb") as f:
+        f.write(b"".join(struct.pack(">I", len(s)) + s for s in seeds))
+    r = subprocess.run([exe, path, "1500000"], capture_output=True, text=True)
+    os.remove(path)
+    tried, fast, bad = (int(x) for x in r.stdout.split())
+    assert r.returncode == 0 and bad == 0, r.stderr[-2000:]
+    assert tried > 1500000 and fast > 100000                     # the fast path is actually exercised

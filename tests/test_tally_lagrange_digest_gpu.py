@@ -213,7 +213,7 @@ def test_pgp_digest_matches_hashlib_and_gpg(engine, golden):
     for i in range(400):
         assert bytes(got[i]) == hashlib.sha256(datas[didx[i]] + sufs[i]).digest()
     # every device hash against hashlib
-    for hid, name in [(2, "sha1"), (8, "sha256"), (9, "sha384"), (10, "sha512"), (11, "sha224")]:
+    for hid, name in [(1, "md5"), (2, "sha1"), (8, "sha256"), (9, "sha384"), (10, "sha512"), (11, "sha224")]:
         got = engine.pgp_digest_batch(datas, sufs, didx, hash_alg=hid)
         for i in range(0, 400, 3):
             assert bytes(got[i]) == hashlib.new(name, datas[didx[i]] + sufs[i]).digest(), (name, i)
