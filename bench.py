@@ -209,20 +209,22 @@ def run_gpu(args, rank, local_rank, world):
     NCALLERS = args.callers
     h_in = [(torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory(), torch.from_numpy(w["sig"]).pin_memory(),
              torch.from_numpy(w["digest"]).pin_memory(), torch.empty(ITEMS, dtype=torch.uint8).pin_memory()) for _ in range(NCALLERS)]
-    for c in range(NCALLERS):
-        for _ in range(args.warmup):
-            eng.rsa_verify_batch(h_in[c][0], h_in[c][1], h_in[c][2], out=h_in[c][3])
-
     def caller(c, n):
         for _ in range(n):
             eng.rsa_verify_batch(h_in[c][0], h_in[c][1], h_in[c][2], out=h_in[c][3])
+
+    def run_callers(fn, shares):
+        ths = [threading.Thread(target=fn, args=(c, shares[c])) for c in range(len(shares))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        torch.cuda.synchronize(dev)
     share = [args.steps // NCALLERS + (1 if c < args.steps % NCALLERS else 0) for c in range(NCALLERS)]
+    # warm-up with the same concurrency as the timed region: the library grows its pool of pinned staging
+    # slots on demand, and callers running together need more of them than one caller alone
+    run_callers(caller, [args.warmup] * NCALLERS)
     barrier()
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=caller, args=(c, share[c])) for c in range(NCALLERS)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    torch.cuda.synchronize(dev)
+    run_callers(caller, share)
     e2e_s = time.perf_counter() - t0
     barrier()
     for c in range(NCALLERS):
@@ -266,22 +268,25 @@ def run_gpu(args, rank, local_rank, world):
     def pgp_caller(c, n):
         for _ in range(n):
             L_.check(eng._lib.bftq_signature_verify_batch(kr._h, vp(ptb), vp(pto), vp(psb), vp(pso), ITEMS, vp(perr[c])))
-    for c in range(PCALLERS):
-        pgp_caller(c, args.warmup)
+    run_callers(pgp_caller, [args.warmup] * PCALLERS)
     pshare = [args.steps // PCALLERS + (1 if c < args.steps % PCALLERS else 0) for c in range(PCALLERS)]
     st0 = eng.stats()
     barrier()
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=pgp_caller, args=(c, pshare[c])) for c in range(PCALLERS)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    torch.cuda.synchronize(dev)
+    run_callers(pgp_caller, pshare)
     pgp_s = time.perf_counter() - t0
     barrier()
     st1 = eng.stats()
     t0 = time.perf_counter()
     pgp_caller(0, 3)
     pgp_single_ms = (time.perf_counter() - t0) / 3 * 1e3
+    # the same leg with the packets parsed by the host packer (BFTQ_GPU_PARSE=0) instead of K0, for context
+    os.environ["BFTQ_GPU_PARSE"] = "0"
+    run_callers(pgp_caller, [args.warmup] * PCALLERS)
+    t0 = time.perf_counter()
+    run_callers(pgp_caller, pshare)
+    host_packer_s = time.perf_counter() - t0
+    del os.environ["BFTQ_GPU_PARSE"]
     for c in range(PCALLERS):
         assert np.array_equal(perr[c] == 0, pw["expect_ok"]), "packet-level results differ from expectation"
     nt_, sec_ = C.c_uint64(), C.c_double()
@@ -290,6 +295,7 @@ def run_gpu(args, rank, local_rank, world):
     pgp_info = {"h2d": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps, "d2h": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps,
                 "launches": (st1["launches"] - st0["launches"]) // args.steps, "threads": int(os.environ["BFTQ_HOST_THREADS"]),
                 "chunks": (st1["packer_chunks"] - st0["packer_chunks"]) // args.steps, "callers": PCALLERS, "single_ms": pgp_single_ms,
+                "host_packer_rate": ITEMS * args.steps / host_packer_s,
                 "thread_ms": {k: (st1["packer_%s_ns" % k] - st0["packer_%s_ns" % k]) / args.steps * 1e-6 for k in ("parse", "stage", "wait")},
                 "packer_only_items_per_sec": ITEMS / sec_.value}
     kr.close()
@@ -422,9 +428,12 @@ def run_gpu(args, rank, local_rank, world):
         "e2e": {"value": total_items / (pgp_ms * 1e-3), "unit": "verifies/s", "ms_per_step": pgp_ms / args.steps,
                 "h2d_bytes_per_step": int(pgp_info["h2d"]), "d2h_bytes_per_step": int(pgp_info["d2h"]),
                 "api": "bftq_signature_verify_batch = crypto.Signature.Verify's batch form (crypto_pgp.go:319-330): OpenPGP signature packets + "
-                       "signed bytes in pageable host memory in, error codes out; packet parsing, keyring lookup, K4 digest + hash-tag check, K1 "
-                       "verify and every copy inside the timed region; %d concurrent callers (one batch each per step)" % pgp_info["callers"],
+                       "signed bytes in pageable host memory in, error codes out; packet parsing + issuer lookup + digest + hash-tag check "
+                       "(K0 on the GPU, flagged items through the host packer + K4), K1 verify and every copy inside the timed region; "
+                       "%d concurrent callers (one batch each per step)" % pgp_info["callers"],
                 "one_caller_ms_per_batch": pgp_info["single_ms"],
+                "gpu_parse": os.environ.get("BFTQ_GPU_PARSE", "1") != "0",
+                "host_packer_verifies_per_sec_rank0": pgp_info["host_packer_rate"],
                 "kernels_per_step": int(pgp_info["launches"]), "host_threads": pgp_info["threads"], "chunks_per_step": int(pgp_info["chunks"]),
                 "worker_thread_ms_per_step": pgp_info["thread_ms"], "packer_only_items_per_sec": pgp_info["packer_only_items_per_sec"],
                 "h2d_gbps_this_box": h2d_gbps, "copy_bound_verifies_per_sec": h2d_gbps * 1e9 / (pgp_info["h2d"] / ITEMS)},

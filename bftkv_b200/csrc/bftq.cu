@@ -1642,12 +1642,13 @@ uint64_t packer_chunk() {
 //                                  (disjoint item ranges, so no locking)
 //   drain(run)                     error path: lets the run's in-flight copies land
 template <typename RunT, typename Submit, typename Retire, typename Drain>
-int run_chunks(bftq_engine* e, uint64_t n_items, unsigned max_threads, uint64_t default_chunk_cap, Submit submit, Retire retire_fn, Drain drain) {
+int run_chunks(bftq_engine* e, uint64_t n_items, unsigned max_threads, uint64_t default_chunk_cap, unsigned chunks_per_worker, Submit submit,
+               Retire retire_fn, Drain drain) {
   const unsigned want = max_threads ? max_threads : packer_threads();
   // Chunk size: small enough that every worker gets several chunks (so its preparation overlaps the kernels
   // of its previous chunks and the GPU starts early), large enough to amortise the per-chunk driver calls.
   uint64_t chunk = packer_chunk();
-  if (!chunk) chunk = std::min<uint64_t>(default_chunk_cap, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * 4) + 63) / 64) * 64));
+  if (!chunk) chunk = std::min<uint64_t>(default_chunk_cap, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * chunks_per_worker) + 63) / 64) * 64));
   const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
   const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, n_chunks));
   const bool tracing = getenv("BFTQ_TRACE") != nullptr;
@@ -1734,7 +1735,7 @@ int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build buil
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count();
   };
   return run_chunks<PlanRun>(
-      e, n_items, max_threads, 4096,
+      e, n_items, max_threads, 4096, 4,
       [&](PlanRun& pr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
         pr.lo = lo; pr.hi = hi;
         pr.pl.reset();
@@ -1888,12 +1889,16 @@ int fast_enqueue(bftq_engine* e, FastRun& fr, const uint8_t* tbs_blob, const uin
   a.out(&d_pre, (uint8_t*)nullptr, n, 0);
   a.out(&d_st, fr.st.data(), n);
   a.out(&d_where, fr.where.data(), n);
+  const bool tracing = getenv("BFTQ_TRACE") != nullptr;
+  const auto c0 = std::chrono::steady_clock::now();
   int rc = a.prepare();
   if (rc) return rc;
+  const auto c1 = std::chrono::steady_clock::now();
   if (tb) memcpy(h_tbs, tbs_blob + t0, tb);
   if (gb) memcpy(h_sig, sig_blob + g0, gb);
   for (size_t i = 0; i <= n; i++) { h_toff[i] = tbs_off[lo + i] - t0; h_soff[i] = sig_off[lo + i] - g0; }
   if (!table.empty()) memcpy(h_tab, table.data(), table.size() * sizeof(bftq::IssuerEntry));
+  const auto c2 = std::chrono::steady_clock::now();
   rc = a.upload();
   if (rc) return rc;
   const int block = 128;
@@ -1903,7 +1908,14 @@ int fast_enqueue(bftq_engine* e, FastRun& fr, const uint8_t* tbs_blob, const uin
   { std::lock_guard<std::mutex> lk(e->mu); e->stats.launches += 1; }
   rc = launch_rsa_any(e, d_kidx, d_pad, d_dig, 8, n, 0, d_pre, d_st, a.stream(), 256);
   if (rc) return rc;
-  return a.download_async();
+  rc = a.download_async();
+  if (tracing) {
+    const auto c3 = std::chrono::steady_clock::now();
+    auto us = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+    size_t nslots; { std::lock_guard<std::mutex> lk(e->mu); nslots = e->slots.size(); }
+    fprintf(stderr, "bftq-trace fast chunk @%llu: slot %.1f us, memcpy %.1f us, enqueue %.1f us, slots %zu\n", (unsigned long long)lo, us(c0, c1), us(c1, c2), us(c2, c3), nslots);
+  }
+  return rc;
 }
 
 bool gpu_parse_enabled() {
@@ -1932,8 +1944,12 @@ static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const ui
     const std::vector<bftq::IssuerEntry> table = build_issuer_table(shared_rings);
     std::mutex fb_mu;
     std::vector<uint64_t> fallback;
+    // The host's share is one memcpy per chunk, so two workers (the caller and one helper) feed the GPU; fewer,
+    // larger chunks keep K1's launches efficient.  More workers bought nothing and on some boxes halved the rate
+    // (profiles/pgp_e2e_experiment_r01.json: 2 callers x 2 workers 46 M/s on every box, x 8 workers 18..42 M/s).
+    const unsigned fast_threads = threads ? threads : std::min(packer_threads(), 2u);
     int rc = run_chunks<FastRun>(
-        kr->e, n_items, threads, 2048,
+        kr->e, n_items, fast_threads, 4096, 2,
         [&](FastRun& fr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
           fr.lo = lo; fr.hi = hi; parse_ns = 0;
           return fast_enqueue(kr->e, fr, tbs_blob, tbs_off, sig_blob, sig_off, table);

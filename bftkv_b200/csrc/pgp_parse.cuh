@@ -50,53 +50,86 @@ pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __
                         const IssuerEntry* __restrict__ issuers, const uint32_t n_issuers,
                         uint32_t* __restrict__ out_key_idx, uint8_t* __restrict__ out_sig /* n x 256 */,
                         uint8_t* __restrict__ out_digest /* n x 32 */, uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where) {
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= n_items) return;
+  const uint32_t item_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = item_raw < n_items;
+  const uint32_t item = live ? item_raw : n_items - 1;        // idle lanes shadow the last item (the warp copies together)
+  const int lane = threadIdx.x & 31;
   const uint64_t s0 = tbs_off[item], s1 = tbs_off[item + 1], g0 = sig_off[item], g1 = sig_off[item + 1];
   const uint8_t* sg = sig_blob + g0;
-  out_key_idx[item] = 0u;
-  auto to_host = [&]() { out_where[item] = kParseHost; out_pre[item] = 6; /* BFTQ_ST_MISSING: K1 leaves the item alone */ };
+  // ---- per item: parse, issuer lookup ---------------------------------------------------------------
+  uint8_t where = kParseDecided, pre = 0;
+  uint32_t kidx = 0;
+  bool copy = false, hash = false;
   fastparse::FastSig f;
-  if (s1 - s0 > 0x3fffffffull || fastparse::parse(sg, (size_t)(g1 - g0), f) != fastparse::kFast) { to_host(); return; }
-  if (f.hash_id != 8 || f.sig_type != 0x00) { to_host(); return; }       // other digests / text mode: host packer (K4 has them all)
-  int hit = -1;
-  for (uint32_t i = 0; i < n_issuers; i++) if (issuers[i].key_id == f.issuer) { hit = (int)i; break; }
-  out_where[item] = kParseDecided;
-  if (hit < 0) { out_pre[item] = 4; return; }                              // BFTQ_ST_UNKNOWN_SIGNER: the stream ends -> ErrUnknownIssuer
-  const IssuerEntry en = issuers[hit];
-  if (en.kind != 0) { to_host(); return; }
-  out_key_idx[item] = en.key_idx;
-  uint8_t pre = 0;
-  if (en.algo != f.pk_algo) pre = 1;                                       // "public key and signature use different algorithms"
-  uint8_t* so = out_sig + (size_t)item * 256;
-  if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }                        // len(sig) != k
+  f.mpi_off = 0; f.mpi_len = 0; f.hashed_off = 0; f.hashed_len = 0; f.tag = 0;
+  if (s1 - s0 > 0x3fffffffull || fastparse::parse(sg, (size_t)(g1 - g0), f) != fastparse::kFast) where = kParseHost;
+  else if (f.hash_id != 8 || f.sig_type != 0x00) where = kParseHost;      // other digests / text mode: host packer (K4 has them all)
   else {
-    const uint32_t padn = 256u - f.mpi_len;
-    for (uint32_t i = 0; i < padn; i++) so[i] = 0;
-    for (uint32_t i = 0; i < f.mpi_len; i++) so[padn + i] = sg[f.mpi_off + i];
+    int hit = -1;
+    for (uint32_t i = 0; i < n_issuers; i++) if (issuers[i].key_id == f.issuer) { hit = (int)i; break; }
+    if (hit < 0) pre = 4;                                                  // BFTQ_ST_UNKNOWN_SIGNER: the stream ends -> ErrUnknownIssuer
+    else {
+      const IssuerEntry en = issuers[hit];
+      if (en.kind != 0) where = kParseHost;
+      else {
+        kidx = en.key_idx;
+        hash = true;
+        if (en.algo != f.pk_algo) pre = 1;                                 // "public key and signature use different algorithms"
+        if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }                  // len(sig) != k
+        else copy = true;
+      }
+    }
   }
-  // digest (K4's SHA-256 arm over three segments) + x/crypto's 16-bit quick check
-  FastSrc src{tbs_blob + s0, sg + f.hashed_off, (uint32_t)(s1 - s0), f.hashed_len, 0};
-  src.total = src.dlen + src.hlen + 6;
-  uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-  const uint32_t nblocks = (src.total + 9 + 63) / 64;
-  for (uint32_t blk = 0; blk < nblocks; blk++) {
-    uint32_t w[16];
+  if (where == kParseHost) pre = 6;                                        // BFTQ_ST_MISSING: K1 leaves the item alone
+  if (!live) copy = false;
+  // ---- per warp: left-pad the signature MPIs into K1's layout (x/crypto padToKeySize), one item at a time,
+  // the 32 lanes writing 4 consecutive bytes each: coalesced stores instead of 256 byte-stores per thread ----
+  const uint64_t src_pos = g0 + f.mpi_off;
+  for (int j = 0; j < 32; j++) {
+    if (!__shfl_sync(0xffffffffu, (int)copy, j)) continue;
+    const uint32_t it = __shfl_sync(0xffffffffu, item, j);
+    const uint32_t len = __shfl_sync(0xffffffffu, f.mpi_len, j);
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)src_pos, j), hi = __shfl_sync(0xffffffffu, (uint32_t)(src_pos >> 32), j);
+    const uint8_t* src = sig_blob + (((uint64_t)hi << 32) | lo);
+    const uint32_t padn = 256u - len;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out_sig + (size_t)it * 256);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
+    for (int t = 0; t < 2; t++) {
+      const uint32_t b0 = (uint32_t)(t * 32 + lane) * 4u;
       uint32_t v = 0;
 #pragma unroll
-      for (int b = 0; b < 4; b++) v = (v << 8) | src.byte(blk * 64 + 4 * i + b);
-      w[i] = v;
+      for (int b = 0; b < 4; b++) {
+        const uint32_t idx = b0 + b;
+        const uint32_t byte = idx >= padn ? (uint32_t)__ldg(src + (idx - padn)) : 0u;
+        v |= byte << (8 * b);
+      }
+      dst[t * 32 + lane] = v;
     }
-    if (blk == nblocks - 1) { w[14] = 0u; w[15] = src.total * 8u; }
-    sha256_compress(h, w);
   }
-  uint8_t* o = out_digest + (size_t)item * 32;
-  for (int i = 0; i < 8; i++)
-    for (int b = 0; b < 4; b++) o[4 * i + b] = (uint8_t)(h[i] >> (24 - 8 * b));
-  if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;                    // BFTQ_ST_HASH_TAG
-  out_pre[item] = pre;
+  // ---- per item: digest (K4's SHA-256 arm over three segments) + x/crypto's 16-bit quick check ----------
+  if (hash && live) {
+    FastSrc src{tbs_blob + s0, sg + f.hashed_off, (uint32_t)(s1 - s0), f.hashed_len, 0};
+    src.total = src.dlen + src.hlen + 6;
+    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    const uint32_t nblocks = (src.total + 9 + 63) / 64;
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) v = (v << 8) | src.byte(blk * 64 + 4 * i + b);
+        w[i] = v;
+      }
+      if (blk == nblocks - 1) { w[14] = 0u; w[15] = src.total * 8u; }
+      sha256_compress(h, w);
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_digest + (size_t)item * 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = __byte_perm(h[i], 0, 0x0123);        // big-endian bytes
+    if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;                   // BFTQ_ST_HASH_TAG
+  }
+  if (live) { out_key_idx[item] = kidx; out_pre[item] = pre; out_where[item] = where; }
 }
 
 }  // namespace bftq

@@ -28,19 +28,23 @@ def main():
     p = lambda a: C.c_void_p(a.ctypes.data)
     rows = []
 
-    def run(chunk, threads, callers, steps=12):
+    def run(chunk, threads, callers, steps=24):
         if chunk:
             os.environ["BFTQ_PLAN_CHUNK"] = str(chunk)
         else:
             os.environ.pop("BFTQ_PLAN_CHUNK", None)
-        os.environ["BFTQ_HOST_THREADS"] = str(threads)
+        if threads:
+            os.environ["BFTQ_HOST_THREADS"] = str(threads)
+        else:
+            os.environ.pop("BFTQ_HOST_THREADS", None)
         errs = [np.zeros(N, np.int32) for _ in range(callers)]
 
         def caller(c, n):
             for _ in range(n):
                 _lib.check(lib.bftq_signature_verify_batch(kr._h, p(tb), p(to), p(sb), p(so), N, p(errs[c])))
-        for c in range(callers):
-            caller(c, 2)
+        ths = [threading.Thread(target=caller, args=(c, 3)) for c in range(callers)]      # warm up with the same concurrency
+        [t.start() for t in ths]
+        [t.join() for t in ths]
         share = [steps // callers + (1 if c < steps % callers else 0) for c in range(callers)]
         t0 = time.perf_counter()
         ths = [threading.Thread(target=caller, args=(c, share[c])) for c in range(callers)]
@@ -49,18 +53,13 @@ def main():
         dt = time.perf_counter() - t0
         for c in range(callers):
             assert np.array_equal(errs[c] == 0, w["expect_ok"])
-        rows.append({"chunk": chunk, "threads": threads, "callers": callers, "verifies_per_sec": N * steps / dt, "ms_per_batch": dt / steps * 1e3})
+        rows.append({"gpu_parse": os.environ.get("BFTQ_GPU_PARSE", "1"), "chunk": chunk, "threads": threads, "callers": callers, "verifies_per_sec": N * steps / dt, "ms_per_batch": dt / steps * 1e3})
         print(rows[-1], file=sys.stderr)
 
-    for chunk in (0, 512, 1024, 2048):
-        run(chunk, 16, 1)
-    for threads in (8, 12, 16, 20):
-        run(0, threads, 1)
-    for callers in (2, 3, 4):
-        run(0, 16, callers)
-    os.environ["BFTQ_BLOCKING_SYNC"] = "1"
-    run(0, 16, 1)
-    run(0, 16, 2)
+    for gp in ("1", "0"):
+        os.environ["BFTQ_GPU_PARSE"] = gp
+        for chunk, threads, callers in ((0, 0, 1), (0, 0, 2), (0, 4, 2), (0, 2, 2), (0, 2, 1), (0, 0, 4)):
+            run(chunk, threads, callers)
     print(json.dumps(rows))
 
 

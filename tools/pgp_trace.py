@@ -27,27 +27,27 @@ for _ in range(3):
     t0 = time.perf_counter()
     call()
     print("untraced call %.3f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
+import threading
+os.environ.pop("BFTQ_HOST_THREADS", None)
+errs = [np.zeros(N, np.int32) for _ in range(2)]
+
+
+def caller(c, n):
+    for _ in range(n):
+        _lib.check(lib.bftq_signature_verify_batch(kr._h, p(tb), p(to), p(sb), p(so), N, p(errs[c])))
+
+
+def both(n):
+    ths = [threading.Thread(target=caller, args=(c, n)) for c in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+
+
+both(5)
+t0 = time.perf_counter()
+both(10)
+print("2 callers untraced: %.3f ms per batch" % ((time.perf_counter() - t0) / 20 * 1e3), file=sys.stderr)
 os.environ["BFTQ_TRACE"] = "1"
 t0 = time.perf_counter()
-call()
-print("traced call %.3f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
-del os.environ["BFTQ_TRACE"]
-# the flat path for comparison, pageable and pinned
-import torch
-from bftkv_b200 import workload as wl
-f = wl.make_verify_batch(N, 16)
-eng.register_rsa_keys([k["n"] for k in f["keys"]], [k["e"] for k in f["keys"]])
-idx = (f["key_idx"] + 16).astype(np.uint32)
-idx[f["expect"] == 4] = 99999
-for pin in (False, True):
-    a = [torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(f["sig"]), torch.from_numpy(f["digest"]), torch.empty(N, dtype=torch.uint8)]
-    if pin:
-        a = [x.pin_memory() for x in a]
-    for _ in range(3):
-        eng.rsa_verify_batch(a[0], a[1], a[2], out=a[3])
-    t0 = time.perf_counter()
-    for _ in range(10):
-        eng.rsa_verify_batch(a[0], a[1], a[2], out=a[3])
-    dt = (time.perf_counter() - t0) / 10
-    assert np.array_equal(a[3].numpy(), f["expect"])
-    print("flat call, pinned=%s: %.3f ms  (%.1f M/s)" % (pin, dt * 1e3, N / dt / 1e6), file=sys.stderr)
+both(2)
+print("2 callers traced: %.3f ms per batch" % ((time.perf_counter() - t0) / 4 * 1e3), file=sys.stderr)
