@@ -1947,7 +1947,8 @@ static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const ui
     // The host's share is one memcpy per chunk, so two workers (the caller and one helper) feed the GPU; fewer,
     // larger chunks keep K1's launches efficient.  More workers bought nothing and on some boxes halved the rate
     // (profiles/pgp_e2e_experiment_r01.json: 2 callers x 2 workers 46 M/s on every box, x 8 workers 18..42 M/s).
-    const unsigned fast_threads = threads ? threads : std::min(packer_threads(), 2u);
+    unsigned fast_threads = threads ? threads : std::min(packer_threads(), 2u);
+    if (const char* v = getenv("BFTQ_FAST_THREADS")) { const int x = atoi(v); if (x > 0) fast_threads = (unsigned)std::min(x, 64); }
     int rc = run_chunks<FastRun>(
         kr->e, n_items, fast_threads, 4096, 2,
         [&](FastRun& fr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {

@@ -56,10 +56,15 @@ def main():
         rows.append({"gpu_parse": os.environ.get("BFTQ_GPU_PARSE", "1"), "chunk": chunk, "threads": threads, "callers": callers, "verifies_per_sec": N * steps / dt, "ms_per_batch": dt / steps * 1e3})
         print(rows[-1], file=sys.stderr)
 
-    for gp in ("1", "0"):
+    for gp, ft, callers in (("1", 8, 2), ("1", 2, 2), ("1", 8, 1), ("1", 2, 1), ("1", 4, 4), ("0", 0, 2), ("0", 0, 4), ("0", 0, 1)):
         os.environ["BFTQ_GPU_PARSE"] = gp
-        for chunk, threads, callers in ((0, 0, 1), (0, 0, 2), (0, 4, 2), (0, 2, 2), (0, 2, 1), (0, 0, 4)):
-            run(chunk, threads, callers)
+        if ft:
+            os.environ["BFTQ_FAST_THREADS"] = str(ft)
+        else:
+            os.environ.pop("BFTQ_FAST_THREADS", None)
+        run(0, 0, callers)
+        rows[-1]["fast_threads"] = ft
+        rows[-1]["cuda_device_max_connections"] = os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "default (8)")
     print(json.dumps(rows))
 
 
