@@ -641,11 +641,32 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* d_pubkeys, uint
   if (n_items == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
   const int block = 128;
-  bftq::ed25519_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, (cudaStream_t)cuda_stream>>>(
-      d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_status);
-  CU(cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // Signatures that share keys (OpenPGP: a handful of keys, many signatures) pay the doublings once per key: window
+  // tables for -A of every key and for the base point (82 KB each, stream-ordered scratch), then at most 128 table
+  // additions per signature.  With few signatures per key the classic double-and-add kernel is cheaper.
+  static const bool no_tables = [] { const char* v = getenv("BFTQ_ED25519_TABLES"); return v && atoi(v) == 0; }();
+  const bool windowed = !no_tables && n_keys > 0 && n_keys <= 4096 && n_items >= 64ull * ((uint64_t)n_keys + 1);
+  int launches = 1;
+  if (windowed) {
+    bftq::ed::gec* d_tab = nullptr;
+    uint8_t* d_ok = nullptr;
+    const size_t tab_bytes = ((size_t)n_keys + 1) * bftq::ed::kEdTableEntries * sizeof(bftq::ed::gec);
+    CU(cudaMallocAsync((void**)&d_tab, tab_bytes + n_keys, st));
+    d_ok = reinterpret_cast<uint8_t*>(d_tab) + tab_bytes;
+    bftq::ed25519_table_kernel<<<n_keys + 1, 64, 0, st>>>(d_pubkeys, n_keys, d_tab, d_ok);
+    bftq::ed25519_verify_windowed_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(
+        d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_tab, d_ok, d_status);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_tab, st));
+    launches = 2;
+  } else {
+    bftq::ed25519_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(
+        d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_status);
+    CU(cudaGetLastError());
+  }
   std::lock_guard<std::mutex> g(e->mu);
-  e->stats.launches += 1;
+  e->stats.launches += launches;
   e->stats.items += n_items;
   return BFTQ_OK;
 }

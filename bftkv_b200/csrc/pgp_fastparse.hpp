@@ -11,9 +11,9 @@
 #include <cstdint>
 
 #if defined(__CUDACC__)
-#define BFTQ_HD __host__ __device__ __forceinline__
+#define BFTQ_FP_HD __host__ __device__ __forceinline__
 #else
-#define BFTQ_HD inline
+#define BFTQ_FP_HD inline
 #endif
 
 namespace bftq { namespace fastparse {
@@ -29,7 +29,7 @@ struct FastSig {
 };
 
 // pgp::parse_subpackets, same accept / reject decisions.
-BFTQ_HD int subpackets(const uint8_t* a, uint32_t n, bool hashed, bool& has_ctime, bool& has_issuer, uint64_t& issuer) {
+BFTQ_FP_HD int subpackets(const uint8_t* a, uint32_t n, bool hashed, bool& has_ctime, bool& has_issuer, uint64_t& issuer) {
   uint32_t p = 0;
   while (p < n) {
     uint32_t l;
@@ -61,7 +61,7 @@ BFTQ_HD int subpackets(const uint8_t* a, uint32_t n, bool hashed, bool& has_ctim
   return kFast;
 }
 
-BFTQ_HD int parse(const uint8_t* d, size_t n, FastSig& out) {
+BFTQ_FP_HD int parse(const uint8_t* d, size_t n, FastSig& out) {
   if (n < 2 || n > 0x7fffffffu) return kFallback;
   const uint8_t hdr = d[0];
   if (!(hdr & 0x80)) return kFallback;

@@ -117,6 +117,51 @@ def test_rfc8032_vectors_and_openssl(host):
         assert host.ed_verify_core_host(s0, badpk, hashlib.sha512(s0[:32] + badpk + m0).digest()) == 0
 
 
+def test_windowed_core_equals_classic_core(host):
+    """The per-key window-table verification (what the batch kernel runs when signatures share keys) against the
+    classic double-and-add core, OpenSSL and the RFC 8032 vectors: valid, bit-flipped, S >= L, undecodable A,
+    small-order A and R, and scalars whose signed digits carry all the way up."""
+    import ctypes
+    host.ed_signed_digits_host.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    rng = random.Random(11)
+    for _ in range(300):                                  # the recoding: sum e_i 16^i == s, e_i in [-8, 8]
+        s = rng.choice([rng.randrange(L), L - 1, 0, 1, 2 ** 252, int("8" * 63, 16) % L, int("7" * 63, 16), 2 ** 252 + 2 ** 251])
+        buf = ctypes.create_string_buffer(64)
+        host.ed_signed_digits_host(s.to_bytes(32, "little"), buf)
+        digs = [b - 256 if b > 127 else b for b in buf.raw]
+        assert all(-8 <= d <= 8 for d in digs) and sum(d * 16 ** i for i, d in enumerate(digs)) == s
+    for pk, msg, sig in RFC8032:
+        pk, msg, sig = bytes.fromhex(pk), bytes.fromhex(msg), bytes.fromhex(sig)
+        assert host.ed_verify_windowed_host(sig, pk, hashlib.sha512(sig[:32] + pk + msg).digest()) == 1
+    sks, pks, kidx, msg, sig, rng = make_sigs(400, 6, 7)
+    order = sorted(range(400), key=lambda i: kidx[i])       # the harness caches the last key's table
+    n_ok = 0
+    for i in order:
+        pk, m = pks[kidx[i]], msg[i].tobytes()
+        s = bytearray(sig[i].tobytes())
+        if i % 3 == 1:
+            s[rng.randrange(64)] ^= 1 << rng.randrange(8)
+        if i % 7 == 3:                                     # S + L: same residue, non-canonical
+            S = int.from_bytes(s[32:], "little") + L
+            if S < 2 ** 256:
+                s[32:] = S.to_bytes(32, "little")
+        s = bytes(s)
+        k = hashlib.sha512(s[:32] + pk + m).digest()
+        a, b = host.ed_verify_core_host(s, pk, k), host.ed_verify_windowed_host(s, pk, k)
+        assert a == b == int(openssl_ok(sks[kidx[i]], s, m)), i
+        n_ok += a
+    assert 150 < n_ok < 400
+    s0, m0 = sig[0].tobytes(), msg[0].tobytes()
+    weird = [(P + 1).to_bytes(32, "little"), (2).to_bytes(32, "little"), b"\xff" * 32,
+             (1).to_bytes(32, "little"),                    # the identity (order 1)
+             (P - 1).to_bytes(32, "little"),                # (0, -1): order 2
+             bytes(32)]                                      # y = 0: order 4
+    for badpk in weird:
+        for sg in (s0, bytes(32) + bytes(32), (1).to_bytes(32, "little") + bytes(32)):
+            k = hashlib.sha512(sg[:32] + badpk + m0).digest()
+            assert host.ed_verify_core_host(sg, badpk, k) == host.ed_verify_windowed_host(sg, badpk, k), (badpk.hex(), sg.hex())
+
+
 @pytest.mark.gpu
 def test_ed25519_gpu_batch(engine):
     n = 4096
@@ -129,9 +174,21 @@ def test_ed25519_gpu_batch(engine):
     unk = [5, 77, 901]
     kidx[unk] = 99
     expect[unk] = 4
-    pk_arr = np.frombuffer(b"".join(pks), np.uint8).reshape(15, 32).copy()
-    got = engine.ed25519_verify_batch(pk_arr, kidx, sig, msg)
+    # a 16th key that does not decode to a curve point: everything under it is invalid (both kernels)
+    bad_key = [11, 500, 3000]
+    kidx[bad_key] = 15
+    expect[bad_key] = 1
+    pk_arr = np.frombuffer(b"".join(pks) + (2).to_bytes(32, "little"), np.uint8).reshape(16, 32).copy()
+    got = engine.ed25519_verify_batch(pk_arr, kidx, sig, msg)          # 4096 signatures, 16 keys: the window-table kernel
     assert np.array_equal(got, expect)
     assert (got == 0).sum() > 2500 and (got == 1).sum() > 1000
-    for size in (1, 2, 31, 129):
+    for size in (1, 2, 31, 129):                                        # few signatures per key: the double-and-add kernel
         assert np.array_equal(engine.ed25519_verify_batch(pk_arr, kidx[:size].copy(), sig[:size].copy(), msg[:size].copy()), expect[:size])
+    # every signature under its own key (no sharing): classic kernel at size
+    sks2, pks2, kidx2, msg2, sig2, _ = make_sigs(300, 300, 5)
+    kidx2 = np.arange(300, dtype=np.uint32)
+    for i in range(300):
+        sig2[i] = np.frombuffer(sks2[i].sign(msg2[i].tobytes()), np.uint8)
+    sig2[7, 3] ^= 4
+    got2 = engine.ed25519_verify_batch(np.frombuffer(b"".join(pks2), np.uint8).reshape(300, 32).copy(), kidx2, sig2, msg2)
+    assert got2[7] == 1 and got2.sum() == 1
