@@ -322,6 +322,7 @@ class Arena {
   // in cudaStreamSynchronize: the packer's workers share the host's CPU quota with the threads still parsing.
   void set_sleepy(bool v) { sleepy_ = v; }
   int finish() {
+    if (!s_) return BFTQ_OK;                          // nothing was enqueued (prepare() failed or was never called)
     if (sleepy_ && recorded_) CU(cudaEventSynchronize(s_->done));
     else CU(cudaStreamSynchronize(s_->stream));
     for (auto* b : bounce_) memcpy(b->host, s_->h_pinned + b->off, b->copy);

@@ -281,3 +281,40 @@ def pgp_canon(data: bytes) -> bytes:
         else:
             out.append(data[i]); i += 1
     return bytes(out)
+
+
+def test_concurrent_batch_callers_share_the_pool():
+    """Four threads call Signature.Verify's batch form at once (what concurrent server handlers do): the calls
+    share the engine's worker pool and staging slots; every caller must get exactly the single-caller answers,
+    through K0 and through the host packer."""
+    import threading
+    w = _pgp_batch(6000, n_keys=8)
+    e = Engine(0)
+    kr = Keyring(e)
+    kr.register(w["keyring"])
+    sig = Signature(kr)
+    for gpu_parse in ("1", "0"):
+        os.environ["BFTQ_GPU_PARSE"] = gpu_parse
+        try:
+            outs, errs = [None] * 4, []
+
+            def caller(c):
+                try:
+                    for _ in range(3):
+                        got = sig.verify_batch(w["tbs"], w["sigs"])
+                        ok = np.array([g is None for g in got])
+                        assert np.array_equal(ok, w["expect_ok"])
+                    outs[c] = ok
+                except Exception as ex:                      # surfaces in the main thread below
+                    errs.append(ex)
+            ths = [threading.Thread(target=caller, args=(c,)) for c in range(4)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            assert not errs, errs
+            assert all(o is not None for o in outs)
+        finally:
+            del os.environ["BFTQ_GPU_PARSE"]
+    st = e.stats()
+    assert st["packer_chunks"] > 0
+    kr.close()
+    e.close()
