@@ -221,3 +221,39 @@ def test_c_tally_matches_python(built):
         bad = [Node(ids[p]) for p in range(off[i], off[i + 1]) if st[p] != 0]
         exp = q.is_quorum(ok) | (q.is_threshold(ok) << 1) | (q.is_sufficient(ok) << 2) | (q.reject(bad) << 3)
         assert got[i] == exp, i
+
+
+def test_digestinfo_prefixes_against_openssl():
+    """Every DigestInfo prefix the oracle (and K1's constant table) carries — MD5, SHA-1, SHA-224/256/384/512 —
+    against OpenSSL in both directions: OpenSSL-made signatures verify in the oracle, and signatures made by
+    textbook exponentiation over the oracle's EM verify in OpenSSL."""
+    import hashlib
+    from cryptography.exceptions import InvalidSignature
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding
+    from cryptography.hazmat.primitives.asymmetric.utils import Prehashed
+    from bftkv_b200 import workload
+    from oracle import pgp_oracle as po
+    k = workload.load_keys(1)[0]
+    priv = workload._private_key(k)
+    pub = priv.public_key()
+    algs = {1: hashes.MD5(), 2: hashes.SHA1(), 8: hashes.SHA256(), 9: hashes.SHA384(), 10: hashes.SHA512(), 11: hashes.SHA224()}
+    for hid, alg in algs.items():
+        d = hashlib.new(po.HASH_BY_ID[hid], b"prefix check %d" % hid).digest()
+        try:
+            s = priv.sign(d, padding.PKCS1v15(), Prehashed(alg))
+        except Exception:                                   # an OpenSSL build that refuses to SIGN with MD5 / SHA-1
+            s = None
+        if s is not None:
+            assert po.rsa_verify_pkcs1v15(k["n"], k["e"], hid, d, s)
+            assert not po.rsa_verify_pkcs1v15(k["n"], k["e"], hid, d[:-1] + bytes([d[-1] ^ 1]), s)
+        t = po.DIGEST_PREFIX[hid] + d
+        em = b"\x00\x01" + b"\xff" * (256 - len(t) - 3) + b"\x00" + t
+        raw = pow(int.from_bytes(em, "big"), k["d"], k["n"]).to_bytes(256, "big")
+        assert po.rsa_verify_pkcs1v15(k["n"], k["e"], hid, d, raw)
+        try:
+            pub.verify(raw, d, padding.PKCS1v15(), Prehashed(alg))
+        except InvalidSignature:
+            raise AssertionError("OpenSSL rejects the oracle's EM for hash id %d" % hid)
+        except Exception:
+            pass                                            # verification with this digest disabled in this OpenSSL
