@@ -1288,1018 +1288,9 @@ int bftq_pgp_digest_batch(bftq_engine* e, const uint8_t* data_blob, const uint64
 
 // ---- host packer ------------------------------------------------------------------------------
 }  // extern "C"
-
-struct bftq_keyring {
-  bftq_engine* e = nullptr;
-  std::mutex mu;
-  std::vector<bftq::pgp::Entity> secring, keyring;
-};
-
-namespace {
-namespace pg = bftq::pgp;
-
-// Enter an RSA key in the engine's table (deduplicated).  Returns -1 when the size is not built.
-int32_t engine_key_index(bftq_engine* e, const pg::PubKey& k) {
-  if (!e) return -1;
-  if (!(k.algo == 1 || k.algo == 2 || k.algo == 3)) return -1;
-  if (!bftq::class_of((int)(k.nbits + 7) / 8) || k.n_be.empty() || !(k.n_be.back() & 1) || k.e == 0) return -1;
-  std::string id((const char*)k.n_be.data(), k.n_be.size());
-  id.append((const char*)&k.e, 4);
-  {
-    std::lock_guard<std::mutex> g(e->mu);
-    auto it = e->key_lookup.find(id);
-    if (it != e->key_lookup.end()) return (int32_t)it->second;
-  }
-  uint8_t n_be[512];
-  memset(n_be, 0, 512);
-  memcpy(n_be + 512 - k.n_be.size(), k.n_be.data(), k.n_be.size());
-  uint32_t first = 0;
-  if (bftq_register_rsa_keys_k(e, n_be, 512, &k.e, 1, &first) != BFTQ_OK) return -1;
-  std::lock_guard<std::mutex> g(e->mu);
-  e->key_lookup[id] = first;
-  return (int32_t)first;
-}
-int32_t dsa_key_index(bftq_engine* e, const pg::PubKey& k) {
-  const auto &P = k.dsa[0], &Q = k.dsa[1], &G = k.dsa[2], &Y = k.dsa[3];
-  if (P.empty() || Q.empty() || G.size() > P.size() || Y.size() > P.size()) return -1;
-  const int cls = dsa_key_class(P.data(), (uint32_t)P.size(), Q.data(), (uint32_t)Q.size());
-  if (cls == 2) return -1;
-  std::string id;
-  for (int i = 0; i < 4; i++) { id.append((const char*)k.dsa[i].data(), k.dsa[i].size()); id.push_back((char)0xff); id.push_back((char)i); }
-  std::lock_guard<std::mutex> g(e->mu);
-  auto it = e->dsa_lookup.find(id);
-  if (it != e->dsa_lookup.end()) return (int32_t)it->second;
-  bftq_engine::DsaKey dk;
-  dk.p = P; dk.q = Q; dk.cls = cls;
-  dk.gy.assign(2 * P.size(), 0);
-  memcpy(dk.gy.data() + P.size() - G.size(), G.data(), G.size());
-  memcpy(dk.gy.data() + 2 * P.size() - Y.size(), Y.data(), Y.size());
-  e->dsa_keys.push_back(dk);
-  e->dsa_lookup[id] = (uint32_t)e->dsa_keys.size() - 1;
-  return (int32_t)e->dsa_keys.size() - 1;
-}
-int32_t any_key_index(bftq_engine* e, const pg::PubKey& k) {
-  if (!e) return -1;
-  if (k.algo == 19) return k.ec_xy.size() == 64 ? 0 : -1;       // P-256 keys travel with their tuples, no table
-  if (k.algo == 17) return dsa_key_index(e, k);
-  return engine_key_index(e, k);
-}
-void index_entity_keys(bftq_engine* e, pg::Entity& ent) {
-  ent.primary.table_idx = any_key_index(e, ent.primary);
-  for (auto& sk : ent.subkeys) sk.key.table_idx = any_key_index(e, sk.key);
-}
-
-struct Tuple {
-  uint32_t item, call;         // item = index inside the plan (chunk-local)
-  int32_t key_idx;
-  uint32_t kbytes;             // RSA: key-size class of the candidate key (signature is padded to it); DSA: key table index
-  uint64_t signer_id;          // primary key id of the candidate key's entity
-  uint32_t data_idx;
-  uint32_t suffix_pos, suffix_len;   // into Plan::suffix_blob
-  uint32_t sig_pos;            // into Plan::sig_blob, sig_bytes_of(alg, kbytes) bytes
-  uint16_t tag;
-  uint8_t pre;                 // status decided on the host (0 = ask the GPU)
-  uint8_t hash_id;
-  uint8_t alg;                 // 1: RSA (K1), 19: ECDSA P-256 (K1c), 17: DSA (K1d)
-};
-// Bytes a tuple occupies in the signature blob.  RSA: the signature padded to the key size.
-// ECDSA: r (32) || s (32) || X (32) || Y (32).  DSA: r (32) || s (32).
-inline uint32_t sig_bytes_of(uint8_t alg, uint32_t kbytes) { return alg == 19 ? 128u : (alg == 17 ? 64u : kbytes); }
-
-struct Plan {
-  std::vector<Tuple> tuples;
-  std::vector<uint32_t> calls_per_item;     // number of CheckDetachedSignature calls that reached a known issuer
-  std::vector<uint8_t> item_failed;          // Verify mode: a structural error / unknown issuer ended the stream
-  std::vector<uint8_t> suffix_blob;
-  std::vector<uint8_t> sig_blob;
-  std::vector<uint8_t> data_blob;            // tbs strings, plus CRLF-canonicalised copies when needed
-  std::vector<uint64_t> data_off;
-  void reset() {
-    tuples.clear(); calls_per_item.clear(); item_failed.clear(); suffix_blob.clear(); sig_blob.clear(); data_blob.clear();
-    data_off.clear(); data_off.push_back(0);
-  }
-};
-
-void canonical_text(const uint8_t* d, size_t n, std::vector<uint8_t>& out) {
-  for (size_t i = 0; i < n; i++) {
-    if (d[i] == 0x0d && i + 1 < n && d[i + 1] == 0x0a) { out.push_back(0x0d); out.push_back(0x0a); i++; }
-    else if (d[i] == 0x0a) { out.push_back(0x0d); out.push_back(0x0a); }
-    else out.push_back(d[i]);
-  }
-}
-
-// Parses item `i`'s signature stream against `rings`.  collective = CollectiveSignature.Verify's
-// tolerant loop (crypto_pgp.go:485-500), else Signature.Verify's strict one (:319-330).
-void plan_item(Plan& pl, uint32_t item, const uint8_t* tbs, size_t tbs_len, const uint8_t* sig, size_t sig_len,
-               const std::vector<const std::vector<pg::Entity>*>& rings, bool collective) {
-  static thread_local std::vector<uint8_t> scratch;
-  static thread_local std::vector<pg::KeyRef> keys;
-  const uint32_t data_plain = (uint32_t)pl.data_off.size() - 1;
-  pl.data_blob.insert(pl.data_blob.end(), tbs, tbs + tbs_len);
-  pl.data_off.push_back(pl.data_blob.size());
-  int32_t data_text = -1;
-  pg::Reader r{sig, sig_len, 0};
-  pg::SigPacket sp;
-  uint32_t calls = 0;
-  bool failed = false;
-  while (r.remaining() > 0) {
-    const int rc = pg::next_known_signature(r, rings, sp, keys, scratch);
-    if (rc == pg::kOk) {
-      const uint32_t spos = (uint32_t)pl.suffix_blob.size(), slen = (uint32_t)sp.suffix_size();
-      pl.suffix_blob.resize((size_t)spos + slen);
-      sp.write_suffix(pl.suffix_blob.data() + spos);
-      uint32_t didx = data_plain;
-      uint8_t common_pre = 0;
-      // v4 and v3 (packet.SignatureV3 -> VerifySignatureV3: same digest rule, the suffix is sig type + creation time)
-      if (sp.sig_type == 0x01) {
-        if (data_text < 0) {
-          std::vector<uint8_t> t;
-          canonical_text(tbs, tbs_len, t);
-          data_text = (int32_t)pl.data_off.size() - 1;
-          pl.data_blob.insert(pl.data_blob.end(), t.begin(), t.end());
-          pl.data_off.push_back(pl.data_blob.size());
-        }
-        didx = (uint32_t)data_text;
-      } else if (sp.sig_type != 0x00) common_pre = BFTQ_ST_BAD_SIGNATURE;       // hashForSignature: unsupported type
-      if (!common_pre && !(sp.pk_algo == 1 || sp.pk_algo == 3 || sp.pk_algo == 17 || sp.pk_algo == 19)) common_pre = BFTQ_ST_UNSUPPORTED;
-      if (!common_pre && !bftq::digest_on_device(sp.hash_id)) common_pre = BFTQ_ST_UNSUPPORTED;     // RIPEMD-160: crypto.RIPEMD160 is not linked into bftkv -> "hash function unavailable"
-      for (const pg::KeyRef& kr : keys) {
-        Tuple t;
-        t.item = item; t.call = calls; t.signer_id = kr.entity->primary.key_id;
-        t.tag = (uint16_t)((sp.hash_tag[0] << 8) | sp.hash_tag[1]);
-        t.data_idx = didx; t.suffix_pos = spos; t.suffix_len = slen;
-        t.pre = common_pre;
-        t.hash_id = sp.hash_id;
-        t.key_idx = kr.key->table_idx;
-        if (!t.pre && kr.key->algo != sp.pk_algo) t.pre = BFTQ_ST_BAD_SIGNATURE;   // "different algorithms"
-        if (!t.pre && t.key_idx < 0) t.pre = BFTQ_ST_UNSUPPORTED;                   // key size not built
-        if (t.key_idx < 0) t.key_idx = 0;
-        t.alg = 1; t.kbytes = 0;
-        size_t key_len = 0;
-        const bool ec = sp.pk_algo == 19 && kr.key->algo == 19, dsa = sp.pk_algo == 17 && kr.key->algo == 17;
-        if (ec) t.alg = 19;
-        else if (dsa) { t.alg = 17; t.kbytes = (uint32_t)t.key_idx; }
-        else {
-          key_len = (kr.key->nbits + 7) / 8;                                          // pub.Size()
-          const int cls = bftq::class_of((int)key_len);
-          t.kbytes = (uint32_t)(cls ? cls : 256);                                     // travels in its size class
-          if (!cls) key_len = 256;
-        }
-        const uint32_t nb = sig_bytes_of(t.alg, t.kbytes);
-        t.sig_pos = (uint32_t)pl.sig_blob.size();
-        pl.sig_blob.resize((size_t)t.sig_pos + nb);                                   // zero-filled
-        uint8_t* dst = pl.sig_blob.data() + t.sig_pos;
-        if (ec || dsa) {           // ecdsa.Verify / dsa.Verify: r, s >= N resp. q (any longer than 32 bytes) fail
-          if (sp.r.size() > 32 || sp.s.size() > 32) { if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE; }
-          else {
-            if (sp.r.size()) memcpy(dst + 32 - sp.r.size(), sp.r.data(), sp.r.size());
-            if (sp.s.size()) memcpy(dst + 64 - sp.s.size(), sp.s.data(), sp.s.size());
-          }
-          if (ec && kr.key->ec_xy.size() == 64) memcpy(dst + 64, kr.key->ec_xy.data(), 64);
-        } else {
-          if (sp.mpi.size() <= key_len) { if (sp.mpi.size()) memcpy(dst + t.kbytes - sp.mpi.size(), sp.mpi.data(), sp.mpi.size()); }   // padToKeySize
-          else if (!t.pre) t.pre = BFTQ_ST_BAD_SIGNATURE;                             // len(sig) != k
-        }
-        pl.tuples.push_back(t);
-      }
-      calls++;
-    } else if (collective) {
-      continue;                      // errors are ignored; the offending packet (or the rest) was consumed
-    } else {
-      failed = true;
-      break;
-    }
-  }
-  pl.calls_per_item.push_back(calls);
-  pl.item_failed.push_back(failed ? 1 : 0);
-}
-
-// One (hash algorithm, signature algorithm, key-size class) group of a plan in flight on its own
-// stream: digest (K4) -> tag check -> verify (K1 / K1c / K1d).
-struct GroupRun {
-  uint32_t hash_alg = 0; int alg = 0; int kb = 0;
-  std::vector<uint32_t> sel;                 // tuple indices of the group, plan order
-  std::unique_ptr<Arena> arena;              // null: every status was decided on the host
-  std::vector<uint8_t> st;                   // statuses come back here
-};
-
-// Composes the group's flat inputs directly in the staging slot's pinned memory, uploads them and
-// enqueues the kernels and the status download on the slot's stream.  Does not wait.
-int group_enqueue(bftq_engine* e, const Plan& pl, GroupRun& g, std::vector<uint8_t>& status, bool sleepy) {
-  const uint32_t dsa_idx = (uint32_t)g.kb;
-  const uint32_t hash_alg = g.hash_alg;
-  const int alg = g.alg;
-  const int kb = (int)sig_bytes_of((uint8_t)alg, (uint32_t)g.kb);
-  const std::vector<uint32_t>& sel = g.sel;
-  const size_t nt = sel.size();
-  const int dlen = bftq::host_hash_dlen(hash_alg);
-  if ((alg == 1 && !e->d_keys) || !bftq::digest_on_device(hash_alg)) {   // nothing verifiable: every tuple keeps its host status
-    for (size_t i = 0; i < nt; i++) { const uint8_t pre = pl.tuples[sel[i]].pre; status[sel[i]] = pre ? pre : (uint8_t)BFTQ_ST_UNSUPPORTED; }
-    return BFTQ_OK;
-  }
-  bftq_engine::DsaKey dk;
-  if (alg == 17) {
-    { std::lock_guard<std::mutex> lk(e->mu); if (dsa_idx < e->dsa_keys.size()) dk = e->dsa_keys[dsa_idx]; }
-    if (dk.p.empty() || dk.cls != 0) {                     // q's bit length not a multiple of 8: dsa.Verify is false
-      for (size_t i = 0; i < nt; i++) {
-        const uint8_t pre = pl.tuples[sel[i]].pre;
-        status[sel[i]] = pre ? pre : (uint8_t)(dk.p.empty() ? BFTQ_ST_UNSUPPORTED : BFTQ_ST_BAD_SIGNATURE);
-      }
-      return BFTQ_OK;
-    }
-  }
-  size_t suffix_total = 0;
-  for (size_t i = 0; i < nt; i++) suffix_total += pl.tuples[sel[i]].suffix_len;
-  g.arena.reset(new Arena(e));
-  g.st.assign(nt, 0);
-  Arena& a = *g.arena;
-  a.set_sleepy(sleepy);
-  uint8_t *d_data, *d_suf, *d_pre, *d_sig, *d_dig, *d_st; uint64_t *d_doff, *d_soff; uint32_t *d_didx, *d_kidx; uint16_t* d_tags;
-  uint8_t *h_data, *h_suf, *h_pre, *h_sig; uint64_t *h_doff, *h_soff; uint32_t *h_didx, *h_kidx; uint16_t* h_tags;
-  a.stage(&d_data, &h_data, std::max<size_t>(pl.data_blob.size(), 1));
-  a.stage(&d_doff, &h_doff, pl.data_off.size());
-  a.stage(&d_suf, &h_suf, std::max<size_t>(suffix_total, 1));
-  a.stage(&d_soff, &h_soff, nt + 1);
-  a.stage(&d_didx, &h_didx, nt);
-  a.stage(&d_kidx, &h_kidx, nt);
-  a.stage(&d_tags, &h_tags, nt);
-  a.stage(&d_pre, &h_pre, nt);
-  a.stage(&d_sig, &h_sig, nt * (size_t)kb);
-  a.out(&d_dig, (uint8_t*)nullptr, nt * dlen, 0);          // device-only intermediate
-  uint8_t *d_gy = nullptr, *d_u = nullptr, *d_pow = nullptr, *d_prod = nullptr;
-  if (alg == 17) {
-    a.in(&d_gy, dk.gy.data(), dk.gy.size());
-    a.out(&d_u, (uint8_t*)nullptr, 2 * nt * dk.q.size(), 0);
-    a.out(&d_pow, (uint8_t*)nullptr, 2 * nt * dk.p.size(), 0);
-    a.out(&d_prod, (uint8_t*)nullptr, nt * dk.p.size(), 0);
-  }
-  a.out(&d_st, g.st.data(), nt);
-  int rc = a.prepare();
-  if (rc) return rc;
-  if (!pl.data_blob.empty()) memcpy(h_data, pl.data_blob.data(), pl.data_blob.size());
-  memcpy(h_doff, pl.data_off.data(), pl.data_off.size() * sizeof(uint64_t));
-  // A group that is the whole plan with one suffix per tuple (the common case: one signature packet per
-  // item, one candidate key) takes the plan's blobs as they are.
-  bool whole = nt == pl.tuples.size() && suffix_total == pl.suffix_blob.size() && nt * (size_t)kb == pl.sig_blob.size();
-  if (whole) {
-    size_t pos = 0;
-    for (size_t i = 0; i < nt && whole; i++) { whole = pl.tuples[i].suffix_pos == pos; pos += pl.tuples[i].suffix_len; }
-  }
-  if (whole) {
-    if (suffix_total) memcpy(h_suf, pl.suffix_blob.data(), suffix_total);
-    if (nt) memcpy(h_sig, pl.sig_blob.data(), nt * (size_t)kb);
-  }
-  size_t spos = 0;
-  for (size_t i = 0; i < nt; i++) {
-    const Tuple& t = pl.tuples[sel[i]];
-    h_kidx[i] = (uint32_t)t.key_idx; h_didx[i] = t.data_idx; h_tags[i] = t.tag; h_pre[i] = t.pre;
-    h_soff[i] = spos;
-    if (!whole) {
-      memcpy(h_sig + i * (size_t)kb, pl.sig_blob.data() + t.sig_pos, kb);
-      if (t.suffix_len) memcpy(h_suf + spos, pl.suffix_blob.data() + t.suffix_pos, t.suffix_len);
-    }
-    spos += t.suffix_len;
-  }
-  h_soff[nt] = spos;
-  rc = a.upload();
-  if (rc) return rc;
-  CU(bftq::launch_pgp_digest(hash_alg, d_data, d_doff, d_didx, d_suf, d_soff, nt, d_dig, d_tags, d_pre, a.stream()));
-  { std::lock_guard<std::mutex> lk(e->mu); e->stats.launches += 1; }
-  if (alg == 19) {
-    const int block = 128;
-    bftq::ecdsa_p256_verify_kernel<<<(unsigned)((nt + block - 1) / block), block, 0, a.stream()>>>(
-        d_sig, 0, nullptr, d_sig, d_sig + 32, d_dig, (uint32_t)dlen, nt, d_pre, d_st);
-    CU(cudaGetLastError());
-    std::lock_guard<std::mutex> lk(e->mu);
-    e->stats.launches += 1;
-    e->stats.items += nt;
-  } else if (alg == 17) {
-    rc = dsa_verify_dev(e, dk.p.data(), (uint32_t)dk.p.size(), dk.q.data(), (uint32_t)dk.q.size(), d_gy, d_sig, d_sig + 32, 64, d_dig,
-                        (uint32_t)dlen, nt, d_pre, d_u, d_pow, d_prod, d_st, a.stream());
-    if (rc) return rc;
-  } else {
-    rc = launch_rsa_any(e, d_kidx, d_sig, d_dig, hash_alg, nt, 0, d_pre, d_st, a.stream(), kb);
-    if (rc) return rc;
-  }
-  return a.download_async();
-}
-
-int group_finish(GroupRun& g, std::vector<uint8_t>& status) {
-  if (!g.arena) return BFTQ_OK;
-  int rc = g.arena->finish();
-  for (size_t i = 0; i < g.sel.size(); i++) status[g.sel[i]] = g.st[i];
-  g.arena.reset();
-  return rc;
-}
-
-// A plan (one chunk of a batch call) on the device: its groups run on one stream each.
-struct PlanRun {
-  Plan pl;
-  std::vector<GroupRun> groups;
-  std::vector<uint8_t> status;               // per tuple, BFTQ_ST_*
-  uint64_t lo = 0, hi = 0;                   // the batch items [lo, hi) this plan covers
-};
-
-void split_groups(PlanRun& pr) {
-  const Plan& pl = pr.pl;
-  pr.groups.clear();
-  pr.status.assign(pl.tuples.size(), 0);
-  for (size_t i = 0; i < pl.tuples.size(); i++) {
-    const Tuple& t = pl.tuples[i];
-    GroupRun* g = nullptr;
-    for (auto& c : pr.groups) if (c.hash_alg == t.hash_id && c.alg == (int)t.alg && c.kb == (int)t.kbytes) { g = &c; break; }
-    if (!g) { pr.groups.emplace_back(); g = &pr.groups.back(); g->hash_alg = t.hash_id; g->alg = t.alg; g->kb = (int)t.kbytes; }
-    g->sel.push_back((uint32_t)i);
-  }
-}
-int plan_enqueue(bftq_engine* e, PlanRun& pr, bool sleepy) {
-  split_groups(pr);
-  for (auto& g : pr.groups) { int rc = group_enqueue(e, pr.pl, g, pr.status, sleepy); if (rc) return rc; }
-  return BFTQ_OK;
-}
-int plan_finish(PlanRun& pr) {
-  int rc = BFTQ_OK;
-  for (auto& g : pr.groups) { int r = group_finish(g, pr.status); if (r && !rc) rc = r; }
-  return rc;
-}
-
-// Per item: did call c succeed (any candidate tuple verified) and who signed.
-struct CallResult { bool ok; uint64_t signer; };
-void fold_calls(const Plan& pl, const std::vector<uint8_t>& status, std::vector<std::vector<CallResult>>& out) {
-  out.assign(pl.calls_per_item.size(), {});
-  for (size_t i = 0; i < out.size(); i++) out[i].assign(pl.calls_per_item[i], CallResult{false, 0});
-  for (size_t t = 0; t < pl.tuples.size(); t++) {
-    const Tuple& tp = pl.tuples[t];
-    CallResult& cr = out[tp.item][tp.call];
-    if (!cr.ok && status[t] == 0) { cr.ok = true; cr.signer = tp.signer_id; }
-  }
-}
-
-// Host threads a batch call may use: the CPU quota of the container (not the core count of the box),
-// capped at 16; BFTQ_HOST_THREADS overrides.  Chunk = items per plan; BFTQ_PLAN_CHUNK overrides.
-unsigned packer_threads() {
-  if (const char* s = getenv("BFTQ_HOST_THREADS")) { const int x = atoi(s); if (x > 0) return (unsigned)std::min(x, 64); }
-  static const unsigned n = [] {
-    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
-      char q[32]; unsigned long per = 0;
-      if (fscanf(f, "%31s %lu", q, &per) == 2 && strcmp(q, "max") != 0 && per) hw = std::min<unsigned>(hw, (unsigned)std::max(1L, (long)((atol(q) + per / 2) / per)));
-      fclose(f);
-    }
-    return std::min(hw, 16u);
-  }();
-  return n;
-}
-uint64_t packer_chunk() {
-  if (const char* s = getenv("BFTQ_PLAN_CHUNK")) { const long x = atol(s); if (x > 0) return (uint64_t)x; }
-  return 0;                 // 0: sized per call (run_batch)
-}
-
-// The packer's batch driver.  The batch is cut into chunks; worker threads (the caller plus helpers from the
-// engine's pool) take chunks off a shared counter, and each keeps kDepth runs in flight: while the kernels of
-// its earlier chunks run on their streams the thread prepares the next one, so host work (CPU) and digest +
-// verify (GPU) overlap both across and inside threads.
-//   submit(run, lo, hi, parse_ns)  prepares items [lo, hi) and enqueues their device work (no waiting)
-//   retire(run)                    waits for the run's results and folds them into the caller's outputs
-//                                  (disjoint item ranges, so no locking)
-//   drain(run)                     error path: lets the run's in-flight copies land
-template <typename RunT, typename Submit, typename Retire, typename Drain>
-int run_chunks(bftq_engine* e, uint64_t n_items, unsigned max_threads, uint64_t default_chunk_cap, unsigned chunks_per_worker, Submit submit,
-               Retire retire_fn, Drain drain) {
-  const unsigned want = max_threads ? max_threads : packer_threads();
-  // Chunk size: small enough that every worker gets several chunks (so its preparation overlaps the kernels
-  // of its previous chunks and the GPU starts early), large enough to amortise the per-chunk driver calls.
-  uint64_t chunk = packer_chunk();
-  if (!chunk) chunk = std::min<uint64_t>(default_chunk_cap, std::max<uint64_t>(512, ((n_items / ((uint64_t)std::max(want, 4u) * chunks_per_worker) + 63) / 64) * 64));
-  const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
-  const unsigned nthreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, n_chunks));
-  const bool tracing = getenv("BFTQ_TRACE") != nullptr;
-  const auto call_t0 = std::chrono::steady_clock::now();
-  std::atomic<uint64_t> next{0};
-  std::atomic<int> first_err{BFTQ_OK};
-  std::mutex err_mu;
-  std::string err_text;
-  auto worker = [&]() {
-    if (e) cudaSetDevice(e->device);
-    constexpr int kDepth = 4;                    // runs a worker keeps in flight
-    RunT runs[kDepth];
-    uint64_t run_chunk[kDepth] = {0, 0, 0, 0};
-    uint64_t head = 0, tail = 0;                 // runs[tail % kDepth .. head % kDepth) are in flight
-    auto note = [&](int rc) {
-      if (!rc) return;
-      std::lock_guard<std::mutex> lk(err_mu);
-      if (first_err.load() == BFTQ_OK) { first_err.store(rc); err_text = g_last_error; }
-    };
-    uint64_t parse_ns = 0, stage_ns = 0, wait_ns = 0, chunks = 0;
-    std::vector<std::array<double, 6>> trace;     // BFTQ_TRACE: per chunk (index, start, parsed, enqueued, wait start, wait end) in us
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-      return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count();
-    };
-    auto retire = [&]() {
-      RunT& pv = runs[tail % kDepth];
-      const auto t0 = now();
-      uint64_t w = 0;
-      if (first_err.load() == BFTQ_OK) note(retire_fn(pv, w)); else drain(pv);
-      wait_ns += w;
-      if (tracing) for (auto& tr : trace) if ((uint64_t)tr[0] == run_chunk[tail % kDepth]) { tr[4] = ns(call_t0, t0) * 1e-3; tr[5] = tr[4] + w * 1e-3; }
-      tail++;
-    };
-    for (;;) {
-      const uint64_t c = next.fetch_add(1);
-      if (c >= n_chunks || first_err.load() != BFTQ_OK) break;
-      if (head - tail == kDepth) retire();
-      RunT& pr = runs[head % kDepth];
-      run_chunk[head % kDepth] = c;
-      const auto t0 = now();
-      uint64_t p_ns = 0;
-      note(submit(pr, c * chunk, std::min(n_items, c * chunk + chunk), p_ns));
-      const uint64_t total = ns(t0, now());
-      parse_ns += p_ns; stage_ns += total > p_ns ? total - p_ns : 0; chunks++;
-      if (tracing) trace.push_back({(double)c, ns(call_t0, t0) * 1e-3, (ns(call_t0, t0) + p_ns) * 1e-3, ns(call_t0, now()) * 1e-3, 0.0, 0.0});
-      head++;
-    }
-    while (tail < head) retire();
-    if (tracing) {
-      std::lock_guard<std::mutex> lk(err_mu);
-      for (auto& tr : trace)
-        fprintf(stderr, "bftq-trace chunk %4d thread %zu parse %8.1f..%8.1f enqueued %8.1f wait %8.1f..%8.1f us\n", (int)tr[0],
-                std::hash<std::thread::id>()(std::this_thread::get_id()) % 1000, tr[1], tr[2], tr[3], tr[4], tr[5]);
-    }
-    if (e) {
-      std::lock_guard<std::mutex> lk(e->mu);
-      e->stats.packer_chunks += chunks; e->stats.packer_parse_ns += parse_ns; e->stats.packer_stage_ns += stage_ns; e->stats.packer_wait_ns += wait_ns;
-    }
-  };
-  // The caller works too; nthreads - 1 helpers come from the engine's pool (concurrent calls share its threads,
-  // oldest job first).  Without an engine (parse-only diagnostics) plain threads do.
-  if (nthreads <= 1) worker();
-  else if (e) e->pool.run(nthreads - 1, worker, [&] { return next.load() < n_chunks; });
-  else {
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t + 1 < nthreads; t++) th.emplace_back(worker);
-    worker();
-    for (auto& t : th) t.join();
-  }
-  if (first_err.load() != BFTQ_OK) return fail(first_err.load(), err_text);
-  return BFTQ_OK;
-}
-
-// Host-packer form: build(lo, hi, plan) parses the items, done(planrun) folds the statuses.  e == nullptr: parse only.
-template <typename Build, typename Done>
-int run_batch(bftq_engine* e, uint64_t n_items, unsigned max_threads, Build build, Done done) {
-  // Waiting for a chunk: spinning in cudaStreamSynchronize measured 31 M/s against 24 M/s with a blocking-sync
-  // event (tools/pgp_e2e_experiment.py) — the wake-up latency costs more than the spinning; BFTQ_BLOCKING_SYNC=1
-  // selects the sleeping wait for hosts where the CPU quota is the scarcer resource.
-  const bool sleepy = [] { const char* v = getenv("BFTQ_BLOCKING_SYNC"); return v && atoi(v) > 0; }();
-  auto tick = [] { return std::chrono::steady_clock::now(); };
-  auto since = [](std::chrono::steady_clock::time_point a) {
-    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count();
-  };
-  return run_chunks<PlanRun>(
-      e, n_items, max_threads, 4096, 4,
-      [&](PlanRun& pr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
-        pr.lo = lo; pr.hi = hi;
-        pr.pl.reset();
-        const auto t0 = tick();
-        build(lo, hi, pr.pl);
-        parse_ns = since(t0);
-        if (e) return plan_enqueue(e, pr, sleepy);
-        split_groups(pr);
-        return (int)BFTQ_OK;
-      },
-      [&](PlanRun& pr, uint64_t& wait_ns) {
-        const auto t0 = tick();
-        const int rc = e ? plan_finish(pr) : (int)BFTQ_OK;
-        wait_ns = since(t0);
-        if (!rc) done(pr);
-        return rc;
-      },
-      [&](PlanRun& pr) { for (auto& g : pr.groups) if (g.arena) { g.arena->finish(); g.arena.reset(); } });
-}
-
-int check_blobs(const void* blob, const uint64_t* off, uint64_t n) {
-  if (!off) return 1;
-  for (uint64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) return 1;
-  if (off[n] > off[0] && !blob) return 1;
-  return 0;
-}
-}  // namespace
-
-extern "C" {
-
-int bftq_keyring_create(bftq_engine* e, bftq_keyring** out) {
-  if (!out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");      // e == NULL: parse-only keyring (no device, no verification)
-  auto* kr = new bftq_keyring();
-  kr->e = e;
-  *out = kr;
-  return BFTQ_OK;
-}
-void bftq_keyring_destroy(bftq_keyring* kr) { delete kr; }
-
-int bftq_keyring_add(bftq_keyring* kr, const uint8_t* key_blocks, uint64_t len, int priv, uint32_t* n_entities) {
-  if (!kr || (len && !key_blocks)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::vector<pg::Entity> ents;
-  pg::read_entities(key_blocks, (size_t)len, ents);
-  for (auto& en : ents) index_entity_keys(kr->e, en);
-  std::lock_guard<std::mutex> g(kr->mu);
-  auto& ring = priv ? kr->secring : kr->keyring;
-  for (auto& en : ents) {                                     // replace(), crypto_pgp.go:124-140
-    bool replaced = false;
-    for (auto& old : ring) if (old.primary.key_id == en.primary.key_id) { old = en; replaced = true; break; }
-    if (!replaced) ring.push_back(en);
-  }
-  if (n_entities) *n_entities = (uint32_t)ents.size();
-  return BFTQ_OK;
-}
-
-int bftq_keyring_remove(bftq_keyring* kr, const uint64_t* key_ids, uint32_t n) {
-  if (!kr || (n && !key_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::lock_guard<std::mutex> g(kr->mu);
-  std::vector<pg::Entity> keep;
-  for (auto& en : kr->keyring) {
-    bool drop = false;
-    for (uint32_t i = 0; i < n; i++) drop = drop || key_ids[i] == en.primary.key_id;
-    if (!drop) keep.push_back(en);
-  }
-  kr->keyring.swap(keep);
-  return BFTQ_OK;
-}
-
-int bftq_keyring_ids(bftq_keyring* kr, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
-  if (!kr || !n) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::lock_guard<std::mutex> g(kr->mu);
-  uint32_t c = 0;
-  for (auto* ring : {&kr->secring, &kr->keyring})
-    for (auto& en : *ring) { if (out_ids && c < cap) out_ids[c] = en.primary.key_id; c++; }
-  *n = c;
-  return BFTQ_OK;
-}
-
-int bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
-  if (!kr || !n) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::lock_guard<std::mutex> g(kr->mu);
-  *n = 0;
-  for (auto* ring : {&kr->keyring, &kr->secring})            // getCertById order, crypto_pgp.go:206-219
-    for (auto& en : *ring)
-      if (en.primary.key_id == key_id) {
-        uint32_t c = 0;
-        for (uint64_t id : en.certifiers) { if (out_ids && c < cap) out_ids[c] = id; c++; }
-        *n = c;
-        return BFTQ_OK;
-      }
-  return fail(BFTQ_ERR_INVALID_ARG, "key id not in keyring");
-}
-
-// ---- GPU-parsed fast path of Signature.Verify's batch form (K0, pgp_parse.cuh) -------------------------
-namespace {
-
-// EntityList.KeysByIdUsage(id, KeyFlagSign) for every key id of the keyring, flattened for the device: an id
-// with exactly one usable RSA key of the 2048-bit size class is decided on the GPU, any other id that has
-// candidates is left to the host packer, and an id that is not in the table has no candidates at all.
-std::vector<bftq::IssuerEntry> build_issuer_table(const std::vector<const std::vector<pg::Entity>*>& rings) {
-  std::vector<bftq::IssuerEntry> tab;
-  std::vector<pg::KeyRef> keys;
-  auto add = [&](uint64_t id) {
-    for (auto& en : tab) if (en.key_id == id) return;
-    pg::keys_by_id_usage(rings, id, pg::kKeyFlagSign, keys);
-    if (keys.empty()) return;
-    bftq::IssuerEntry en{};
-    en.key_id = id; en.kind = 1;
-    const pg::PubKey& k = *keys[0].key;
-    const int kb = (int)((k.nbits + 7) / 8);
-    if (keys.size() == 1 && (k.algo == 1 || k.algo == 2 || k.algo == 3) && k.table_idx >= 0 && bftq::class_of(kb) == 256) {
-      en.kind = 0; en.key_idx = (uint32_t)k.table_idx; en.kbytes = (uint16_t)kb; en.algo = k.algo;
-    }
-    tab.push_back(en);
-  };
-  for (auto* ring : rings)
-    for (const pg::Entity& e : *ring) {
-      add(e.primary.key_id);
-      for (const pg::Subkey& sk : e.subkeys) add(sk.key.key_id);
-    }
-  return tab;
-}
-
-struct FastRun {
-  std::unique_ptr<Arena> arena;
-  std::vector<uint8_t> st, where;
-  uint64_t lo = 0, hi = 0;
-};
-
-// Copies the chunk's raw bytes into staging and enqueues K0 (parse + digest) and K1 on the slot's stream.
-int fast_enqueue(bftq_engine* e, FastRun& fr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
-                 const uint64_t* sig_off, const std::vector<bftq::IssuerEntry>& table) {
-  const uint64_t lo = fr.lo, hi = fr.hi;
-  const size_t n = (size_t)(hi - lo);
-  const uint64_t t0 = tbs_off[lo], tb = tbs_off[hi] - t0, g0 = sig_off[lo], gb = sig_off[hi] - g0;
-  fr.arena.reset(new Arena(e));
-  fr.st.assign(n, 0); fr.where.assign(n, 0);
-  Arena& a = *fr.arena;
-  uint8_t *d_tbs, *d_sig, *h_tbs, *h_sig, *d_pad, *d_dig, *d_pre, *d_st, *d_where;
-  uint64_t *d_toff, *d_soff, *h_toff, *h_soff;
-  bftq::IssuerEntry *d_tab, *h_tab;
-  uint32_t* d_kidx;
-  a.stage(&d_tbs, &h_tbs, std::max<size_t>(tb, 1));
-  a.stage(&d_toff, &h_toff, n + 1);
-  a.stage(&d_sig, &h_sig, std::max<size_t>(gb, 1));
-  a.stage(&d_soff, &h_soff, n + 1);
-  a.stage(&d_tab, &h_tab, std::max<size_t>(table.size(), 1));
-  a.out(&d_kidx, (uint32_t*)nullptr, n, 0);                // device-only intermediates: K0 -> K1
-  a.out(&d_pad, (uint8_t*)nullptr, n * 256, 0);
-  a.out(&d_dig, (uint8_t*)nullptr, n * 32, 0);
-  a.out(&d_pre, (uint8_t*)nullptr, n, 0);
-  a.out(&d_st, fr.st.data(), n);
-  a.out(&d_where, fr.where.data(), n);
-  const bool tracing = getenv("BFTQ_TRACE") != nullptr;
-  const auto c0 = std::chrono::steady_clock::now();
-  int rc = a.prepare();
-  if (rc) return rc;
-  const auto c1 = std::chrono::steady_clock::now();
-  if (tb) memcpy(h_tbs, tbs_blob + t0, tb);
-  if (gb) memcpy(h_sig, sig_blob + g0, gb);
-  for (size_t i = 0; i <= n; i++) { h_toff[i] = tbs_off[lo + i] - t0; h_soff[i] = sig_off[lo + i] - g0; }
-  if (!table.empty()) memcpy(h_tab, table.data(), table.size() * sizeof(bftq::IssuerEntry));
-  const auto c2 = std::chrono::steady_clock::now();
-  rc = a.upload();
-  if (rc) return rc;
-  const int block = 128;
-  bftq::pgp_parse_digest_kernel<<<(unsigned)((n + block - 1) / block), block, 0, a.stream()>>>(
-      d_tbs, d_toff, d_sig, d_soff, (uint32_t)n, d_tab, (uint32_t)table.size(), d_kidx, d_pad, d_dig, d_pre, d_where);
-  CU(cudaGetLastError());
-  { std::lock_guard<std::mutex> lk(e->mu); e->stats.launches += 1; }
-  rc = launch_rsa_any(e, d_kidx, d_pad, d_dig, 8, n, 0, d_pre, d_st, a.stream(), 256);
-  if (rc) return rc;
-  rc = a.download_async();
-  if (tracing) {
-    const auto c3 = std::chrono::steady_clock::now();
-    auto us = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
-    size_t nslots; { std::lock_guard<std::mutex> lk(e->mu); nslots = e->slots.size(); }
-    fprintf(stderr, "bftq-trace fast chunk @%llu: slot %.1f us, memcpy %.1f us, enqueue %.1f us, slots %zu\n", (unsigned long long)lo, us(c0, c1), us(c1, c2), us(c2, c3), nslots);
-  }
-  return rc;
-}
-
-bool gpu_parse_enabled() {
-  const char* v = getenv("BFTQ_GPU_PARSE");
-  return !(v && atoi(v) == 0);
-}
-
-}  // namespace
-
-static int verify_batch_impl(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
-                             const uint64_t* sig_off, const uint8_t* cert_blob, const uint64_t* cert_off, uint64_t n_items,
-                             int32_t* out_err, bool parse_only = false, unsigned threads = 0, uint64_t* n_tuples = nullptr,
-                             bool no_gpu_parse = false) {
-  if (!kr || (!out_err && !parse_only)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  if (!kr->e && !parse_only) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
-  if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(sig_blob, sig_off, n_items) || (cert_off && check_blobs(cert_blob, cert_off, n_items)))
-    return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
-  if (n_items == 0) return BFTQ_OK;
-  std::vector<pg::Entity> sec, pub;                         // snapshot: Register / Remove may run concurrently (crypto_pgp.go:142-177)
-  if (!cert_off) { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
-  const std::vector<const std::vector<pg::Entity>*> shared_rings = {&sec, &pub};
-  // Fast path: the packets are parsed and hashed on the GPU (K0) and only the items it flags come back to the
-  // host packer below.  Needs the RSA key table on the device; VerifyWithCertificate (a keyring per item) and
-  // the parse-only diagnostic always take the host packer.
-  if (!cert_off && !parse_only && !no_gpu_parse && gpu_parse_enabled() && kr->e->d_keys && n_items < 0xffffffffull) {
-    const std::vector<bftq::IssuerEntry> table = build_issuer_table(shared_rings);
-    std::mutex fb_mu;
-    std::vector<uint64_t> fallback;
-    // The host's share is one memcpy per chunk, so two workers (the caller and one helper) feed the GPU; fewer,
-    // larger chunks keep K1's launches efficient.  More workers bought nothing and on some boxes halved the rate
-    // (profiles/pgp_e2e_experiment_r01.json: 2 callers x 2 workers 46 M/s on every box, x 8 workers 18..42 M/s).
-    unsigned fast_threads = threads ? threads : std::min(packer_threads(), 2u);
-    if (const char* v = getenv("BFTQ_FAST_THREADS")) { const int x = atoi(v); if (x > 0) fast_threads = (unsigned)std::min(x, 64); }
-    int rc = run_chunks<FastRun>(
-        kr->e, n_items, fast_threads, 4096, 2,
-        [&](FastRun& fr, uint64_t lo, uint64_t hi, uint64_t& parse_ns) {
-          fr.lo = lo; fr.hi = hi; parse_ns = 0;
-          return fast_enqueue(kr->e, fr, tbs_blob, tbs_off, sig_blob, sig_off, table);
-        },
-        [&](FastRun& fr, uint64_t& wait_ns) {
-          const auto t0 = std::chrono::steady_clock::now();
-          const int r = fr.arena->finish();
-          wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-          fr.arena.reset();
-          if (r) return r;
-          std::vector<uint64_t> mine;
-          for (uint64_t i = fr.lo; i < fr.hi; i++) {
-            if (fr.where[i - fr.lo] == bftq::kParseDecided) out_err[i] = fr.st[i - fr.lo] == 0 ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
-            else mine.push_back(i);
-          }
-          if (!mine.empty()) { std::lock_guard<std::mutex> lk(fb_mu); fallback.insert(fallback.end(), mine.begin(), mine.end()); }
-          return (int)BFTQ_OK;
-        },
-        [&](FastRun& fr) { if (fr.arena) { fr.arena->finish(); fr.arena.reset(); } });
-    if (rc) return rc;
-    if (n_tuples) *n_tuples = n_items - fallback.size();
-    if (fallback.empty()) return BFTQ_OK;
-    // the flagged items, in item order, through the host packer
-    std::sort(fallback.begin(), fallback.end());
-    std::vector<uint8_t> tb, sb;
-    std::vector<uint64_t> to{0}, so{0};
-    for (uint64_t i : fallback) {
-      tb.insert(tb.end(), tbs_blob + tbs_off[i], tbs_blob + tbs_off[i + 1]); to.push_back(tb.size());
-      sb.insert(sb.end(), sig_blob + sig_off[i], sig_blob + sig_off[i + 1]); so.push_back(sb.size());
-    }
-    std::vector<int32_t> err(fallback.size(), BFTQ_ERR_INVALID_SIGNATURE);
-    rc = verify_batch_impl(kr, tb.data(), to.data(), sb.data(), so.data(), nullptr, nullptr, fallback.size(), err.data(), false, threads, nullptr, true);
-    if (rc) return rc;
-    for (size_t j = 0; j < fallback.size(); j++) out_err[fallback[j]] = err[j];
-    return BFTQ_OK;
-  }
-  std::atomic<uint64_t> tuples{0};
-  auto build = [&](uint64_t lo, uint64_t hi, Plan& pl) {
-    std::vector<pg::Entity> cert_ring;                      // VerifyWithCertificate: a one-entity ring per item
-    std::vector<const std::vector<pg::Entity>*> rings;
-    for (uint64_t i = lo; i < hi; i++) {
-      if (cert_off) {
-        cert_ring.clear();
-        std::vector<pg::Entity> ents;
-        pg::read_entities(cert_blob + cert_off[i], (size_t)(cert_off[i + 1] - cert_off[i]), ents);
-        if (!ents.empty()) { index_entity_keys(kr->e, ents[0]); cert_ring.push_back(ents[0]); }
-        rings = {&cert_ring};
-      }
-      // (the per-item ring dies with this iteration: a plan keeps copies, never pointers into it; an
-      // empty ring makes every issuer unknown, i.e. the item fails like a missing certificate must)
-      plan_item(pl, (uint32_t)(i - lo), tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), sig_blob + sig_off[i],
-                (size_t)(sig_off[i + 1] - sig_off[i]), cert_off ? rings : shared_rings, false);
-    }
-    tuples.fetch_add(pl.tuples.size());
-  };
-  auto done = [&](PlanRun& pr) {
-    if (!out_err) return;
-    const Plan& pl = pr.pl;
-    const size_t n = (size_t)(pr.hi - pr.lo);
-    // Verify: every call must succeed and there must be at least one ("at least we need one valid signature")
-    std::vector<uint8_t> call_ok;
-    std::vector<uint32_t> call_base(n + 1, 0);
-    for (size_t i = 0; i < n; i++) call_base[i + 1] = call_base[i] + pl.calls_per_item[i];
-    call_ok.assign(call_base[n], 0);
-    for (size_t t = 0; t < pl.tuples.size(); t++)
-      if (pr.status[t] == 0) call_ok[call_base[pl.tuples[t].item] + pl.tuples[t].call] = 1;
-    for (size_t i = 0; i < n; i++) {
-      bool ok = !pl.item_failed[i] && pl.calls_per_item[i] > 0;
-      for (uint32_t c = call_base[i]; c < call_base[i + 1]; c++) ok = ok && call_ok[c];
-      out_err[pr.lo + i] = ok ? 0 : BFTQ_ERR_INVALID_SIGNATURE;
-    }
-  };
-  int rc = run_batch(parse_only ? nullptr : kr->e, n_items, threads, build, done);
-  if (n_tuples) *n_tuples = tuples.load();
-  return rc;
-}
-
-int bftq_signature_parse(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, int collective, uint64_t* out_issuers,
-                         uint8_t* out_hash_ids, uint32_t cap, uint32_t* n_calls, int32_t* failed) {
-  if (!kr || !n_calls || !failed || (sig_len && !sig)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::vector<pg::Entity> sec, pub;
-  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
-  std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
-  pg::Reader r{sig, (size_t)sig_len, 0};
-  std::vector<uint8_t> scratch;
-  std::vector<pg::KeyRef> keys;
-  pg::SigPacket sp;
-  uint32_t calls = 0;
-  *failed = 0;
-  while (r.remaining() > 0) {
-    const int rc = pg::next_known_signature(r, rings, sp, keys, scratch);
-    if (rc == pg::kOk) {
-      if (calls < cap) { if (out_issuers) out_issuers[calls] = sp.issuer; if (out_hash_ids) out_hash_ids[calls] = sp.hash_id; }
-      calls++;
-    } else if (collective) {
-      continue;
-    } else {
-      *failed = 1;
-      break;
-    }
-  }
-  *n_calls = calls;
-  return BFTQ_OK;
-}
-
-int bftq_signature_verify_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
-                                const uint64_t* sig_off, uint64_t n_items, int32_t* out_err) {
-  return verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, nullptr, nullptr, n_items, out_err);
-}
-int bftq_signature_verify_with_cert_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
-                                          const uint8_t* sig_blob, const uint64_t* sig_off, const uint8_t* cert_blob,
-                                          const uint64_t* cert_off, uint64_t n_items, int32_t* out_err) {
-  if (!cert_off) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  return verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, cert_blob, cert_off, n_items, out_err);
-}
-
-int bftq_signature_plan_measure(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* sig_blob,
-                                const uint64_t* sig_off, uint64_t n_items, uint32_t threads, uint64_t* n_tuples, double* seconds) {
-  const auto t0 = std::chrono::steady_clock::now();
-  int rc = verify_batch_impl(kr, tbs_blob, tbs_off, sig_blob, sig_off, nullptr, nullptr, n_items, nullptr, true, threads, n_tuples);
-  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  return rc;
-}
-
-// Signers(): every parseable v4 signature packet whose issuer is a PRIMARY key id of the keyring.
-static int signers_impl(bftq_keyring* kr, const uint8_t* sig, uint64_t len, std::vector<uint64_t>& ids) {
-  std::vector<pg::Entity> sec, pub;
-  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
-  pg::Reader r{sig, (size_t)len, 0};
-  std::vector<uint8_t> scratch;
-  for (;;) {
-    int tag; const uint8_t* body; size_t bl;
-    const int rc = pg::read_packet(r, tag, body, bl, scratch);
-    if (rc) break;                                            // EOF or framing error ends r.Next()'s loop
-    if (!pg::known_tag(tag) || tag != 2) continue;
-    pg::SigPacket sp;
-    if (pg::parse_signature(body, bl, sp)) break;             // parse error: r.Next() returns err -> break
-    if (sp.version != 4) continue;                            // *SignatureV3 is not in the type switch
-    if (!sp.has_issuer) return fail(BFTQ_ERR_MALFORMED, "signature without issuer (the reference dereferences nil here)");
-    bool found = false;                                       // getCertById: keyring first, then secring
-    for (auto& en : pub) found = found || en.primary.key_id == sp.issuer;
-    for (auto& en : sec) found = found || en.primary.key_id == sp.issuer;
-    if (found) ids.push_back(sp.issuer);
-  }
-  return BFTQ_OK;
-}
-
-int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n) {
-  if (!kr || !n || (sig_len && !sig)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::vector<uint64_t> ids;
-  int rc = signers_impl(kr, sig, sig_len, ids);
-  if (rc) return rc;
-  for (uint32_t i = 0; i < ids.size() && i < cap && out_ids; i++) out_ids[i] = ids[i];
-  *n = (uint32_t)ids.size();
-  return BFTQ_OK;
-}
-
-// Node ids -> dense indices, quorum by index, GPU tally (K2) over the verified signers.
-static int sufficient_by_tally(bftq_engine* e, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids, uint32_t n_members,
-                               const std::vector<std::vector<uint64_t>>& signers, std::vector<uint8_t>& bits) {
-  std::map<uint64_t, uint32_t> dense;
-  auto idx_of = [&](uint64_t id) { auto it = dense.find(id); if (it != dense.end()) return it->second; uint32_t v = (uint32_t)dense.size(); dense[id] = v; return v; };
-  std::vector<bftq_qc_t> q(n_qc);
-  std::vector<uint32_t> members(n_members);
-  for (uint32_t m = 0; m < n_members; m++) members[m] = idx_of(member_ids[m]);
-  for (uint32_t c = 0; c < n_qc; c++) q[c] = bftq_qc_t{qcs[c].f, qcs[c].min, qcs[c].threshold, qcs[c].suff, qcs[c].member_off, qcs[c].member_cnt};
-  bftq_quorum* qh = nullptr;
-  int rc = bftq_quorum_create(e, q.data(), n_qc, members.data(), n_members, &qh);
-  if (rc) return rc;
-  std::vector<uint32_t> off(signers.size() + 1, 0), kidx;
-  for (size_t i = 0; i < signers.size(); i++) {
-    for (uint64_t id : signers[i]) kidx.push_back(idx_of(id));
-    off[i + 1] = (uint32_t)kidx.size();
-  }
-  std::vector<uint8_t> st(std::max<size_t>(kidx.size(), 1), 0);
-  if (kidx.empty()) kidx.push_back(0);
-  bits.assign(signers.size(), 0);
-  rc = bftq_tally_batch(e, qh, off.data(), kidx.data(), st.data(), signers.size(), bits.data());
-  bftq_quorum_destroy(e, qh);
-  return rc;
-}
-
-int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
-                                 uint32_t n_members, const uint8_t* tbs_blob, const uint64_t* tbs_off, const uint8_t* ss_blob,
-                                 const uint64_t* ss_off, uint64_t n_items, int32_t* out_err) {
-  if (!kr || !out_err || (n_qc && !qcs) || (n_members && !member_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: verification needs an engine (there is no CPU fallback)");
-  if (check_blobs(tbs_blob, tbs_off, n_items) || check_blobs(ss_blob, ss_off, n_items)) return fail(BFTQ_ERR_INVALID_ARG, "bad blob offsets");
-  if (n_items == 0) return BFTQ_OK;
-  std::vector<pg::Entity> sec, pub;
-  { std::lock_guard<std::mutex> g(kr->mu); sec = kr->secring; pub = kr->keyring; }
-  const std::vector<const std::vector<pg::Entity>*> rings = {&sec, &pub};
-  std::vector<std::vector<uint64_t>> signers(n_items);
-  auto build = [&](uint64_t lo, uint64_t hi, Plan& pl) {
-    for (uint64_t i = lo; i < hi; i++)
-      plan_item(pl, (uint32_t)(i - lo), tbs_blob + tbs_off[i], (size_t)(tbs_off[i + 1] - tbs_off[i]), ss_blob + ss_off[i],
-                (size_t)(ss_off[i + 1] - ss_off[i]), rings, true);
-  };
-  auto done = [&](PlanRun& pr) {
-    std::vector<std::vector<CallResult>> calls;
-    fold_calls(pr.pl, pr.status, calls);
-    for (size_t i = 0; i < calls.size(); i++)
-      for (auto& c : calls[i]) if (c.ok) signers[pr.lo + i].push_back(c.signer);      // no dedupe (crypto_pgp.go:492)
-  };
-  int rc = run_batch(kr->e, n_items, 0, build, done);
-  if (rc) return rc;
-  std::vector<uint8_t> bits;
-  rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
-  if (rc) return rc;
-  for (uint64_t i = 0; i < n_items; i++) out_err[i] = (bits[i] & BFTQ_TALLY_IS_SUFFICIENT) ? 0 : BFTQ_ERR_INSUFFICIENT_SIGS;
-  return BFTQ_OK;
-}
-
-int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
-                                       uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out) {
-  if (!kr || !out || (ss_len && !ss)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  if (!kr->e) return fail(BFTQ_ERR_NO_DEVICE, "parse-only keyring: the sufficiency tally runs on the GPU");
-  std::vector<std::vector<uint64_t>> signers(1);
-  int rc = signers_impl(kr, ss, ss_len, signers[0]);
-  if (rc) return rc;
-  std::vector<uint8_t> bits;
-  rc = sufficient_by_tally(kr->e, qcs, n_qc, member_ids, n_members, signers, bits);
-  if (rc) return rc;
-  *out = (bits[0] & BFTQ_TALLY_IS_SUFFICIENT) ? 1 : 0;
-  return BFTQ_OK;
-}
-
-// ---- batching aggregator ------------------------------------------------------------------------
-}  // extern "C"
-
-struct bftq_aggregator {
-  struct Job {
-    std::vector<uint8_t> tbs, sig, cert;
-    int result = 0;
-    bool done = false;
-  };
-  bftq_keyring* kr = nullptr;
-  uint32_t max_batch = 16384, max_wait_us = 200;
-  std::mutex mu;
-  std::condition_variable cv_work, cv_done;
-  std::vector<std::shared_ptr<Job>> queue;
-  std::chrono::steady_clock::time_point first_at;
-  bool stop = false;
-  uint64_t n_batches = 0, n_items = 0;
-  std::thread worker;
-
-  void flush(std::vector<std::shared_ptr<Job>>& batch) {
-    // split into plain and with-certificate halves, one packer call each
-    for (int with_cert = 0; with_cert < 2; with_cert++) {
-      std::vector<Job*> sel;
-      for (auto& j : batch) if ((j->cert.empty() ? 0 : 1) == with_cert) sel.push_back(j.get());
-      if (sel.empty()) continue;
-      std::vector<uint8_t> tb, sb, cb;
-      std::vector<uint64_t> to{0}, so{0}, co{0};
-      for (Job* j : sel) {
-        tb.insert(tb.end(), j->tbs.begin(), j->tbs.end()); to.push_back(tb.size());
-        sb.insert(sb.end(), j->sig.begin(), j->sig.end()); so.push_back(sb.size());
-        cb.insert(cb.end(), j->cert.begin(), j->cert.end()); co.push_back(cb.size());
-      }
-      std::vector<int32_t> err(sel.size(), BFTQ_ERR_INVALID_SIGNATURE);
-      int rc = with_cert ? bftq_signature_verify_with_cert_batch(kr, tb.data(), to.data(), sb.data(), so.data(), cb.data(), co.data(), sel.size(), err.data())
-                         : bftq_signature_verify_batch(kr, tb.data(), to.data(), sb.data(), so.data(), sel.size(), err.data());
-      for (size_t i = 0; i < sel.size(); i++) sel[i]->result = rc ? rc : err[i];
-    }
-  }
-  void loop() {
-    std::unique_lock<std::mutex> l(mu);
-    for (;;) {
-      cv_work.wait(l, [&] { return stop || !queue.empty(); });
-      if (stop && queue.empty()) return;
-      // wait for the batch to fill up or its deadline to pass
-      const auto deadline = first_at + std::chrono::microseconds(max_wait_us);
-      cv_work.wait_until(l, deadline, [&] { return stop || queue.size() >= max_batch; });
-      std::vector<std::shared_ptr<Job>> batch;
-      batch.swap(queue);
-      l.unlock();
-      flush(batch);
-      l.lock();
-      for (auto& j : batch) j->done = true;
-      n_batches += 1;
-      n_items += batch.size();
-      cv_done.notify_all();
-    }
-  }
-};
-
-extern "C" {
-
-int bftq_aggregator_create(bftq_keyring* kr, uint32_t max_batch, uint32_t max_wait_us, bftq_aggregator** out) {
-  if (!kr || !out || max_batch == 0) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  auto* a = new bftq_aggregator();
-  a->kr = kr; a->max_batch = max_batch; a->max_wait_us = max_wait_us;
-  a->worker = std::thread([a] { a->loop(); });
-  *out = a;
-  return BFTQ_OK;
-}
-void bftq_aggregator_destroy(bftq_aggregator* a) {
-  if (!a) return;
-  { std::lock_guard<std::mutex> l(a->mu); a->stop = true; }
-  a->cv_work.notify_all();
-  a->worker.join();
-  delete a;
-}
-int bftq_aggregator_verify(bftq_aggregator* a, const uint8_t* tbs, uint64_t tbs_len, const uint8_t* sig, uint64_t sig_len,
-                           const uint8_t* cert, uint64_t cert_len) {
-  if (!a || (tbs_len && !tbs) || (sig_len && !sig) || (cert_len && !cert)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  auto j = std::make_shared<bftq_aggregator::Job>();
-  j->tbs.assign(tbs, tbs + tbs_len); j->sig.assign(sig, sig + sig_len);
-  if (cert_len) j->cert.assign(cert, cert + cert_len);
-  std::unique_lock<std::mutex> l(a->mu);
-  if (a->stop) return fail(BFTQ_ERR_INVALID_ARG, "aggregator is shutting down");
-  if (a->queue.empty()) a->first_at = std::chrono::steady_clock::now();
-  a->queue.push_back(j);
-  a->cv_work.notify_all();
-  a->cv_done.wait(l, [&] { return j->done; });
-  return j->result;
-}
-int bftq_aggregator_stats(bftq_aggregator* a, uint64_t* n_batches, uint64_t* n_items) {
-  if (!a) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-  std::lock_guard<std::mutex> l(a->mu);
-  if (n_batches) *n_batches = a->n_batches;
-  if (n_items) *n_items = a->n_items;
-  return BFTQ_OK;
-}
+#include "packer_host.inc"
 
 // ---- quorum-descriptor builder ------------------------------------------------------------------
-}  // extern "C"
 struct bftq_graph { std::mutex mu; bftq::wot::Graph g; };
 extern "C" {
 int bftq_graph_create(bftq_graph** out) {
