@@ -206,7 +206,7 @@ def run_gpu(args, rank, local_rank, world):
     # transport/transport.go:110-127; the C ABI is re-entrant): while one call's kernel runs, the
     # other call's H2D copy is in flight.  Every step still copies its full inputs H2D and its
     # status bytes D2H inside the timed region.
-    NCALLERS = args.callers
+    NCALLERS = max(1, min(args.callers, host_cores() // world))
     h_in = [(torch.from_numpy(w["key_idx"].astype(np.int32)).pin_memory(), torch.from_numpy(w["sig"]).pin_memory(),
              torch.from_numpy(w["digest"]).pin_memory(), torch.empty(ITEMS, dtype=torch.uint8).pin_memory()) for _ in range(NCALLERS)]
     def caller(c, n):
@@ -261,7 +261,8 @@ def run_gpu(args, rank, local_rank, world):
     kr.register(pw["keyring"])
     ptb, pto = _blob(pw["tbs"])
     psb, pso = _blob(pw["sigs"])
-    PCALLERS = max(1, args.pgp_callers)
+    # each caller brings one helper thread (K0 path): on a rank that owns few host cores more callers only spin
+    PCALLERS = max(1, min(args.pgp_callers, pthreads // 2))
     perr = [np.zeros(ITEMS, np.int32) for _ in range(PCALLERS)]
     vp = lambda a: C.c_void_p(a.ctypes.data)
 
