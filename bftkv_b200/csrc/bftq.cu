@@ -175,6 +175,7 @@ struct bftq_engine {
   size_t d_keys_cap = 0;
   std::vector<bftq::r32::RsaKey32> h_keys32;     // radix-2^32 constants of the same keys
   bftq::r32::RsaKey32* d_keys32 = nullptr;
+  std::vector<void*> retired;                    // device key tables replaced by larger ones (freed at shutdown)
   bool all_2048 = true;                          // every registered modulus has exactly 2048 bits
   int rsa_kernel = 0;                            // 0 auto, 28 force radix-2^28, 32 force radix-2^32 (env BFTQ_RSA_KERNEL)
   std::vector<StagingSlot*> slots;
@@ -479,6 +480,7 @@ void bftq_shutdown(bftq_engine* e) {
   }
   if (e->d_keys) cudaFree(e->d_keys);
   if (e->d_keys32) cudaFree(e->d_keys32);
+  for (void* p : e->retired) cudaFree(p);
   delete e;
 }
 
@@ -554,15 +556,16 @@ int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t strid
   e->h_keys32.insert(e->h_keys32.end(), fresh32.begin(), fresh32.end());
   e->all_2048 = e->all_2048 && fresh_all_2048;
   if (e->h_keys.size() > e->d_keys_cap) {
-    // Kernels in flight may still read the old table: synchronise before replacing it.
-    CU(cudaDeviceSynchronize());
+    // Kernels in flight — or being launched right now by other callers, with the old pointer already read — may
+    // still use the old table: it is retired, not freed (2.4 KB per key; released at bftq_shutdown), so growing the
+    // keyring while batches are being verified is safe.
     size_t cap = std::max<size_t>(64, e->h_keys.size() * 2);
     bftq::RsaKeyDev* nd = nullptr;
     bftq::r32::RsaKey32* nd32 = nullptr;
     CU(cudaMalloc((void**)&nd, cap * sizeof(bftq::RsaKeyDev)));
     CU(cudaMalloc((void**)&nd32, cap * sizeof(bftq::r32::RsaKey32)));
-    if (e->d_keys) cudaFree(e->d_keys);
-    if (e->d_keys32) cudaFree(e->d_keys32);
+    if (e->d_keys) e->retired.push_back(e->d_keys);
+    if (e->d_keys32) e->retired.push_back(e->d_keys32);
     e->d_keys = nd;
     e->d_keys32 = nd32;
     e->d_keys_cap = cap;
