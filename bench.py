@@ -28,9 +28,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# The library keeps one stream per chunk in flight (16-32 at a time); with the default of 8 hardware queues streams
-# share queues and a long kernel in one delays the copies of another.  Must be set before the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 MACS_PER_VERIFY = 156864          # 19 Montgomery products x (2*64^2 + 64) word-MACs, SURVEY §8(d)
 NCU_DRAM_BYTES_PER_LAUNCH = 19272448      # profiles/ncu_rsa_verify_r01c_r32.txt: 19.272448 MB read + 0 B written per 65536-item launch

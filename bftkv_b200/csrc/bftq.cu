@@ -440,9 +440,6 @@ const char* bftq_last_error(void) { return g_last_error.c_str(); }
 int bftq_init(int device, bftq_engine** out) {
   if (!out) return fail(BFTQ_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
-  // One stream per chunk in flight: ask for the maximum number of hardware queues unless the process has chosen
-  // (takes effect only if no CUDA context exists yet; the default of 8 makes streams share queues).
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
   if (ce != cudaSuccess || count == 0)
