@@ -255,7 +255,7 @@ def run_gpu(args, rank, local_rank, world):
     from bftkv_b200 import _lib as L_
     from bftkv_b200.crypto_gpu import Keyring, _blob
     pthreads = max(1, host_cores() // world)
-    os.environ.setdefault("BFTQ_HOST_THREADS", str(min(16, pthreads)))
+    os.environ.setdefault("BFTQ_HOST_THREADS", str(min(16, max(1, pthreads - 2))))       # leave the callers' own threads inside the CPU quota
     pw = workload.make_pgp_verify_batch(ITEMS, NKEYS, seed=0xBF7C0002 + rank, corrupt_seed=0xBF7C0003 + rank, threads=pthreads)
     kr = Keyring(eng)
     kr.register(pw["keyring"])
