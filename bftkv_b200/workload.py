@@ -201,3 +201,53 @@ def make_pgp_verify_batch(n_items: int, n_keys: int = 16, seed: int = 0xBF7C0002
         list(ex.map(work, [(lo, min(n_items, lo + step)) for lo in range(0, n_items, step)]))
     return {"keyring": b"".join(blocks[:n_keys]), "key_ids": kids[:n_keys], "outsider_block": blocks[n_keys],
             "tbs": tbs, "sigs": sigs, "expect_ok": ~(bad | unk), "key_idx": key_idx}
+
+
+# ---- hand-built signature packets of the rarer kinds (v3 packets, any digest) for the parity tests ----------------
+# DigestInfo prefixes: Go crypto/rsa hashPrefixes == crypto/threshold/rsa/rsa.go:345-354, by OpenPGP hash id.
+_DIGESTINFO = {
+    1: "3020300c06082a864886f70d020505000410", 2: "3021300906052b0e03021a05000414", 3: "3021300906052b2403020105000414",
+    8: "3031300d060960864801650304020105000420", 9: "3041300d060960864801650304020205000430",
+    10: "3051300d060960864801650304020305000440", 11: "302d300d06096086480165030402040500041c"}
+_HASHLIB = {1: "md5", 2: "sha1", 3: "ripemd160", 8: "sha256", 9: "sha384", 10: "sha512", 11: "sha224"}
+
+
+def raw_rsa_sign(k, hash_id: int, digest: bytes) -> int:
+    """EMSA-PKCS1-v1_5 signature by textbook exponentiation (k carries d): works for digests OpenSSL refuses to sign."""
+    t = bytes.fromhex(_DIGESTINFO[hash_id]) + digest
+    klen = (k["n"].bit_length() + 7) // 8
+    em = b"\x00\x01" + b"\xff" * (klen - len(t) - 3) + b"\x00" + t
+    return pow(int.from_bytes(em, "big"), k["d"], k["n"])
+
+
+def canonical_text(data: bytes) -> bytes:
+    """Text-mode canonicalisation as x/crypto's canonicalTextHash does it: bare LF -> CRLF, CRLF kept."""
+    out, i = bytearray(), 0
+    while i < len(data):
+        if data[i] == 0x0D and i + 1 < len(data) and data[i + 1] == 0x0A:
+            out += b"\r\n"; i += 2
+        elif data[i] == 0x0A:
+            out += b"\r\n"; i += 1
+        else:
+            out.append(data[i]); i += 1
+    return bytes(out)
+
+
+def sig_packet_v3(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_type: int = 0) -> bytes:
+    """A version-3 RSA signature packet (RFC 4880 §5.2.2): digest = H(data || sig type || creation time).
+    `data` is signed as given for sig_type 0 and after text canonicalisation for sig_type 1."""
+    signed = canonical_text(data) if sig_type == 1 else data
+    suffix = bytes([sig_type]) + struct.pack(">I", ctime)
+    d = hashlib.new(_HASHLIB[hash_id], signed + suffix).digest()
+    body = bytes([3, 5]) + suffix + struct.pack(">Q", key_id) + bytes([1, hash_id]) + d[:2] + _mpi(raw_rsa_sign(k, hash_id, d))
+    return _old_packet(2, body)
+
+
+def sig_packet_v4(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_type: int = 0) -> bytes:
+    """A version-4 RSA signature packet with any digest (hashed: creation time; unhashed: issuer)."""
+    signed = canonical_text(data) if sig_type == 1 else data
+    hashed = bytes([5, 2]) + struct.pack(">I", ctime)
+    head = bytes([4, sig_type, 1, hash_id]) + struct.pack(">H", len(hashed)) + hashed
+    d = hashlib.new(_HASHLIB[hash_id], signed + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
+    unhashed = bytes([9, 16]) + struct.pack(">Q", key_id)
+    return _old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + d[:2] + _mpi(raw_rsa_sign(k, hash_id, d)))

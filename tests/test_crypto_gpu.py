@@ -199,35 +199,6 @@ def test_signature_verify_big_batch_chunked_threads():
 
 # ---- v3 signature packets and MD5 (what foreign keys / old implementations may send) -----------------
 
-def _raw_rsa_sign(k, hash_id, digest):
-    """PKCS#1 v1.5 signature by textbook exponentiation (the key dict carries d)."""
-    t = pgp.DIGEST_PREFIX[hash_id] + digest
-    klen = (k["n"].bit_length() + 7) // 8
-    em = b"\x00\x01" + b"\xff" * (klen - len(t) - 3) + b"\x00" + t
-    return pow(int.from_bytes(em, "big"), k["d"], k["n"])
-
-
-def _sig_v3(k, key_id, hash_id, data, ctime, sig_type=0):
-    import hashlib
-    import struct
-    from bftkv_b200 import workload
-    suffix = bytes([sig_type]) + struct.pack(">I", ctime)
-    d = hashlib.new(pgp.HASH_BY_ID[hash_id], data + suffix).digest()
-    body = bytes([3, 5]) + suffix + struct.pack(">Q", key_id) + bytes([1, hash_id]) + d[:2] + workload._mpi(_raw_rsa_sign(k, hash_id, d))
-    return workload._old_packet(2, body)
-
-
-def _sig_v4(k, key_id, hash_id, data, ctime, sig_type=0):
-    import hashlib
-    import struct
-    from bftkv_b200 import workload
-    hashed = bytes([5, 2]) + struct.pack(">I", ctime)
-    head = bytes([4, sig_type, 1, hash_id]) + struct.pack(">H", len(hashed)) + hashed
-    d = hashlib.new(pgp.HASH_BY_ID[hash_id], data + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
-    unhashed = bytes([9, 16]) + struct.pack(">Q", key_id)
-    return workload._old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + d[:2] + workload._mpi(_raw_rsa_sign(k, hash_id, d)))
-
-
 def test_v3_signatures_and_md5():
     """packet.SignatureV3 (digest = H(data || sig type || creation time)) and MD5 / SHA-1 / SHA-2 digests through
     Signature.Verify, binary and text mode, valid and corrupted — decisions equal the oracle's restatement of
@@ -246,20 +217,20 @@ def test_v3_signatures_and_md5():
     sig = Signature(kr)
     tbs, sigs = [], []
     j = 0
-    for maker in (_sig_v3, _sig_v4):
+    for maker in (workload.sig_packet_v3, workload.sig_packet_v4):
         for hid in (1, 2, 8, 9, 10, 11):
             for sig_type in (0, 1):
                 for bad in (False, True):
                     i = j % 3
                     data = b"line one\nline two\r\nvalue %d" % j
-                    pkt = bytearray(maker(keys[i], kids[i], hid, pgp_canon(data) if sig_type == 1 else data, 0x5F000000 + j, sig_type))
+                    pkt = bytearray(maker(keys[i], kids[i], hid, data, 0x5F000000 + j, sig_type))
                     if bad:
                         pkt[-5] ^= 0x02
                     tbs.append(data); sigs.append(bytes(pkt))
                     j += 1
     # a v3 and a v4 packet in one stream (Verify: all must be valid), and a v3 packet with an unknown issuer first
-    tbs.append(b"both"); sigs.append(_sig_v3(keys[0], kids[0], 8, b"both", 1) + _sig_v4(keys[1], kids[1], 1, b"both", 2))
-    tbs.append(b"skip"); sigs.append(_sig_v3(keys[0], 0x1122334455667788, 8, b"skip", 1) + _sig_v3(keys[2], kids[2], 2, b"skip", 3))
+    tbs.append(b"both"); sigs.append(workload.sig_packet_v3(keys[0], kids[0], 8, b"both", 1) + workload.sig_packet_v4(keys[1], kids[1], 1, b"both", 2))
+    tbs.append(b"skip"); sigs.append(workload.sig_packet_v3(keys[0], 0x1122334455667788, 8, b"skip", 1) + workload.sig_packet_v3(keys[2], kids[2], 2, b"skip", 3))
     got = sig.verify_batch(tbs, sigs)
     n_ok = 0
     for t, s, g in zip(tbs, sigs, got):
@@ -269,18 +240,6 @@ def test_v3_signatures_and_md5():
     assert n_ok == 24 + 2
     kr.close()
     e.close()
-
-
-def pgp_canon(data: bytes) -> bytes:
-    out, i = bytearray(), 0
-    while i < len(data):
-        if data[i] == 0x0D and i + 1 < len(data) and data[i + 1] == 0x0A:
-            out += b"\r\n"; i += 2
-        elif data[i] == 0x0A:
-            out += b"\r\n"; i += 1
-        else:
-            out.append(data[i]); i += 1
-    return bytes(out)
 
 
 def test_concurrent_batch_callers_share_the_pool():

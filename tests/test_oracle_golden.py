@@ -257,3 +257,43 @@ def test_digestinfo_prefixes_against_openssl():
             raise AssertionError("OpenSSL rejects the oracle's EM for hash id %d" % hid)
         except Exception:
             pass                                            # verification with this digest disabled in this OpenSSL
+
+
+def test_v3_and_v4_hand_built_packets_against_gpg(tmp_path):
+    """The packet makers the GPU parity tests use (bftkv_b200/workload.py: v3 and v4 RSA signature packets, binary
+    and text mode, SHA-1/SHA-2 digests) produce signatures GnuPG accepts, and the oracle agrees with GnuPG on every
+    one of them, valid and corrupted — so the oracle's v3 digest rule (H(data || sig type || creation time),
+    packet.SignatureV3 / VerifySignatureV3) and its text canonicalisation are pinned on an independent tool.
+    MD5 is left to the DigestInfo test above: GnuPG 2.4 refuses MD5 signatures outright."""
+    import os
+    import subprocess
+    from bftkv_b200 import workload
+    from oracle import pgp_oracle as po
+    k = workload.load_keys(1)[0]
+    priv = workload._private_key(k)
+    blk, kid = workload.pgp_public_key_block(k, priv, b"v3 pin <v3@bftq.test>")
+    ents = po.read_entities(blk)
+    home = str(tmp_path)
+    os.chmod(home, 0o700)
+    env = dict(os.environ, GNUPGHOME=home)
+    (tmp_path / "k").write_bytes(blk)
+    r = subprocess.run(["gpg", "--batch", "--import", str(tmp_path / "k")], env=env, capture_output=True, text=True)
+    assert "imported: 1" in r.stderr, r.stderr
+    n = 0
+    for maker in (workload.sig_packet_v3, workload.sig_packet_v4):
+        for hid in (2, 8, 9, 10, 11):
+            for sig_type in (0, 1):
+                for bad in (False, True):
+                    data = b"line one\nline two\r\nlast line %d" % n
+                    pkt = bytearray(maker(k, kid, hid, data, 0x5F000000 + n, sig_type))
+                    if bad:
+                        pkt[-7] ^= 0x10
+                    (tmp_path / "m").write_bytes(data)
+                    (tmp_path / "s").write_bytes(bytes(pkt))
+                    g = subprocess.run(["gpg", "--batch", "--verify", str(tmp_path / "s"), str(tmp_path / "m")], env=env,
+                                       capture_output=True, text=True)
+                    good = "Good signature" in g.stderr
+                    assert good == (not bad), (maker.__name__, hid, sig_type, bad, g.stderr[-300:])
+                    assert (po.signature_verify(ents, data, bytes(pkt)) is None) == good
+                    n += 1
+    assert n == 40
