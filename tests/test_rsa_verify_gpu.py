@@ -213,3 +213,32 @@ def test_roundtrip_property_fresh_keys(built):
     got = e.rsa_verify_batch(w["key_idx"], w["sig"], w["digest"])
     assert np.array_equal(got, w["expect"]) and 1500 < int(got.sum()) < 2600
     e.close()
+
+
+@pytest.mark.skipif(os.environ.get("BFTQ_TEST_R32SQ") != "1",
+                    reason="experimental squaring kernel (BFTQ_RSA_KERNEL=r32sq): opt in with BFTQ_TEST_R32SQ=1 until it has been validated on a GPU")
+def test_experimental_squaring_kernel_bit_exact(batch64k, built):
+    """rsa_square_r32.cuh (dedicated Montgomery squaring, emulated limb for limb by tools/emu_sq.py) against the
+    oracle on config 2, ragged sizes and the edge values of s."""
+    w = batch64k
+    ns, es = [k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]]
+    os.environ["BFTQ_RSA_KERNEL"] = "r32sq"
+    try:
+        e = Engine(0)
+    finally:
+        del os.environ["BFTQ_RSA_KERNEL"]
+    e.register_rsa_keys(ns, es)
+    ref = c_oracle.rsa_verify_batch(ns, es, w["key_idx"], w["sig"], w["digest"], threads=NCPU)
+    got = e.rsa_verify_batch(w["key_idx"], w["sig"], w["digest"])
+    assert np.array_equal(got, ref)
+    for n in (1, 7, 8, 9, 33, 1000):
+        assert np.array_equal(e.rsa_verify_batch(w["key_idx"][:n].copy(), w["sig"][:n].copy(), w["digest"][:n].copy()), ref[:n])
+    kidx = np.zeros(6, np.uint32)
+    dig = w["digest"][:6].copy()
+    sig = np.zeros((6, 256), np.uint8)
+    for i, v in enumerate([0, 1, ns[0] - 1, ns[0], 2 ** 2048 - 1, 2 ** 2047]):
+        sig[i] = np.frombuffer(int(v).to_bytes(256, "big"), np.uint8)
+    got = e.rsa_verify_batch(kidx, sig, dig)
+    exp = [0 if pgp.rsa_verify_pkcs1v15(ns[0], es[0], 8, dig[i].tobytes(), sig[i].tobytes()) else 1 for i in range(6)]
+    assert got.tolist() == exp
+    e.close()

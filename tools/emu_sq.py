@@ -113,3 +113,154 @@ if __name__ == "__main__":
     for u, t in enumerate(tab0):
         print("unit %d (lane %d %s):" % (u, u % 4, "lo" if u < 4 else "hi"),
               ", ".join("lane%d.slot%d[%d:+%d]->%d%s" % (L, s, o, ln, d, "x2" if dbl else "") for L, s, o, ln, d, dbl in t))
+
+
+# ---- limb-level emulation: the same chains, accumulators and carries the CUDA code will use ---------------------
+def chain16(acc, base, x_limbs, m):
+    """Chain<16>::run(p = acc + base, carry limbs acc[base+16], acc[base+17], operands x_limbs (8 of them), m)."""
+    c = 0
+    for k in range(8):
+        lo = base + 2 * k
+        v = acc[lo] + (acc[lo + 1] << 32) + x_limbs[k] * m + c
+        acc[lo] = v & (B - 1); acc[lo + 1] = (v >> 32) & (B - 1); c = v >> 64
+    for k in (base + 16, base + 17):
+        v = acc[k] + c
+        acc[k] = v & (B - 1); c = v >> 32
+    assert c == 0
+
+
+def block_mul(x, rows):
+    """acc = x (16 limbs) * rows (NR limbs): per row an even chain (x0, x2, ..) at offset i and an odd chain
+    (x1, x3, ..) at offset i + 1, one accumulator of NR + 19 limbs."""
+    nr = len(rows)
+    acc = [0] * (nr + 19)
+    for i, m in enumerate(rows):
+        chain16(acc, i, x[0::2], m)
+        chain16(acc, i + 1, x[1::2], m)
+    assert all(v == 0 for v in acc[nr + 16:])
+    return acc[:nr + 16]
+
+
+SLOT_LEN = (32, 32, 24)
+SLOT_BASE = (0, 32, 64)            # word offsets of the three slot results in a lane's shared-memory column
+
+
+def mont_sqr_limbs(a, n, n0inv, table):
+    al = [limbs(a, 64)[16 * L:16 * L + 16] for L in range(T4)]
+    nl = [limbs(n, 64)[16 * L:16 * L + 16] for L in range(T4)]
+    # slots -> shared memory (one 88-word column per lane)
+    sm = []
+    for L in range(T4):
+        cpy = al[L & 1]
+        src = al[L | 2]
+        rows2 = src[:8] if L < 2 else src[8:]
+        col = block_mul(al[L], al[L]) + block_mul(al[L], al[(L + 1) % 4]) + block_mul(cpy, rows2)
+        assert len(col) == 88
+        sm.append(col)
+    # unit sums: 16 limbs + overflow word, contributions added once or twice, predicated per position
+    unit, ov = [None] * 8, [0] * 8
+    for u in range(8):
+        v = [0] * 16
+        o = 0
+        for (L, slot, off, ln, dst, dbl) in table[u]:
+            for _ in range(2 if dbl else 1):
+                c = 0
+                for p in range(16):
+                    w = sm[L][SLOT_BASE[slot] + off + p - dst] if dst <= p < dst + ln else 0
+                    s = v[p] + w + c
+                    v[p] = s & (B - 1); c = s >> 32
+                o += c
+        unit[u], ov[u] = v, o
+    # carry normalisation, lo units (lanes 0..3) then hi units, as mont_mul's tail does it
+    def normalise(vs, hs, carry_into_first):
+        fb = [carry_into_first] + hs[:3]
+        g, ones = [0] * 4, [False] * 4
+        for r in range(4):
+            c = fb[r]
+            for p in range(16):
+                s = vs[r][p] + c
+                vs[r][p] = s & (B - 1); c = s >> 32
+            g[r] = c
+            ones[r] = all(x == B - 1 for x in vs[r])
+        cin_ = [0] * 5
+        for r in range(1, 5):
+            cin_[r] = g[r - 1] | (1 if ones[r - 1] and cin_[r - 1] else 0)
+        for r in range(4):
+            c = cin_[r]
+            for p in range(16):
+                s = vs[r][p] + c
+                vs[r][p] = s & (B - 1); c = s >> 32
+        return hs[3] + cin_[4]
+    top_lo = normalise(unit[:4], ov[:4], 0)
+    top_hi = normalise(unit[4:], ov[4:], top_lo)
+    assert top_hi == 0
+    tval = sum(val(unit[u]) << (512 * u) for u in range(8))
+    assert tval == a * a
+    # reduction: E/O/Z/cin as in mont_mul, the a x b chains gone, the high units fed in at the top lane
+    E = [unit[r] + [0, 0, 0] for r in range(T4)]
+    O = [[0] * 17 for _ in range(T4)]
+    cin = [0] * T4
+    Z = [0] * T4
+    def chain(arr, idxpairs, xs, m, c=0):
+        for lo, xi in idxpairs:
+            v = arr[lo] + (arr[lo + 1] << 32) + xs[xi] * m + c
+            arr[lo] = v & (B - 1); arr[lo + 1] = (v >> 32) & (B - 1); c = v >> 64
+        return c
+    def end(arr, idx, c, n2):
+        for k in range(n2):
+            v = arr[idx + k] + c; arr[idx + k] = v & (B - 1); c = v >> 32
+        assert c == 0
+    for owner in range(T4):
+        for jj in range(0, W, 2):
+            q0 = ((E[0][0] + Z[0] + cin[0]) & (B - 1)) * n0inv & (B - 1)
+            for r in range(T4):
+                c = chain(E[r], [(k, k) for k in range(0, W, 2)], nl[r], q0, cin[r]); end(E[r], 16, c, 2)
+                c = chain(O[r], [(k - 1, k) for k in range(1, W, 2)], nl[r], q0); end(O[r], 16, c, 1)
+            s0 = [E[r][0] + Z[r] for r in range(T4)]
+            c0 = [x >> 32 for x in s0]; p0 = [x & (B - 1) for x in s0]
+            q1 = ((E[0][1] + O[0][0] + c0[0]) & (B - 1)) * n0inv & (B - 1)
+            p1 = [0] * T4
+            for r in range(T4):
+                c = chain(O[r], [(k, k) for k in range(0, W, 2)], nl[r], q1); end(O[r], 16, c, 1)
+                c = chain(E[r], [(k + 1, k) for k in range(1, W, 2)], nl[r], q1); end(E[r], 18, c, 1)
+                s = E[r][1] + O[r][0] + c0[r]; p1[r] = s & (B - 1); cin[r] = s >> 32
+            assert p0[0] == 0 and p1[0] == 0
+            f0, f1 = unit[4 + owner][jj], unit[4 + owner][jj + 1]
+            for r in range(T4):
+                r0 = p0[r + 1] if r < T4 - 1 else f0
+                r1 = p1[r + 1] if r < T4 - 1 else f1
+                Z[r] = O[r][1]
+                E[r] = E[r][2:] + [0, 0]; O[r] = O[r][2:] + [0, 0]
+                v = E[r][14] + (E[r][15] << 32) + (E[r][16] << 64) + (E[r][17] << 96) + r0 + (r1 << 32)
+                E[r][14] = v & (B - 1); E[r][15] = (v >> 32) & (B - 1); E[r][16] = (v >> 64) & (B - 1); E[r][17] = (v >> 96) & (B - 1)
+    tot = 0
+    for r in range(T4):
+        loc = cin[r] + Z[r] + sum(E[r][k] << (32 * k) for k in range(19)) + sum(O[r][k] << (32 * (k + 1)) for k in range(17))
+        assert E[r][17] == 0 and E[r][18] == 0 and O[r][15] == 0 and O[r][16] == 0 and E[r][16] <= 4, (E[r][16:], O[r][15:])
+        tot += loc << (32 * W * r)
+    return tot
+
+
+def run_limb_level():
+    random.seed(3)
+    R = 1 << 2048
+    _, table = scatter(square_blocks(random.getrandbits(2048))[0])
+    for it in range(200):
+        n = random.getrandbits(2048) | (1 << 2047) | 1
+        a = random.getrandbits(2048)
+        if it % 7 == 0:
+            a = R - 1
+        if it % 11 == 0:
+            n = R - 1
+        if it % 13 == 0:
+            a = (1 << 2048) - (1 << 1024) - 1
+        if it % 17 == 0:
+            a = 0
+        n0inv = (-pow(n, -1, B)) % B
+        got = mont_sqr_limbs(a, n, n0inv, table)
+        assert got == (a * a + ((a * a * (-pow(n, -1, R))) % R) * n) // R and got < R + n, it
+    print("limb-level squaring emulation ok")
+
+
+if __name__ == "__main__":
+    run_limb_level()
