@@ -20,7 +20,7 @@ int main() {
     if (!d.empty()) { int m = rng() % 5; for (int i = 0; i < m; i++) d[rng() % d.size()] ^= 1 << (rng() % 8); if (rng() % 4 == 0) d.resize(rng() % d.size()); }
     // exact-size heap copy so ASAN sees any overread
     uint8_t* buf = new uint8_t[d.size() ? d.size() : 1];
-    memcpy(buf, d.data(), d.size());
+    if (!d.empty()) memcpy(buf, d.data(), d.size());
     Reader r{buf, d.size(), 0};
     std::vector<uint8_t> scratch; std::vector<KeyRef> keys; SigPacket sp;
     while (r.remaining() > 0) { int rc = next_known_signature(r, rings, sp, keys, scratch); if (rc == kOk) calls++; else if (rc == kEof) break; }
