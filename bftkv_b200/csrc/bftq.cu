@@ -4,7 +4,6 @@
 #include "../../include/bftq.h"
 #include "rsa_verify.cuh"
 #include "rsa_verify_r32.cuh"
-#include "rsa_square_r32.cuh"
 #include "tally.cuh"
 #include "lagrange.cuh"
 #include "modexp.cuh"
@@ -178,7 +177,7 @@ struct bftq_engine {
   bftq::r32::RsaKey32* d_keys32 = nullptr;
   std::vector<void*> retired;                    // device key tables replaced by larger ones (freed at shutdown)
   bool all_2048 = true;                          // every registered modulus has exactly 2048 bits
-  int rsa_kernel = 0;                            // 0 auto, 28 force radix-2^28, 32 force radix-2^32 (env BFTQ_RSA_KERNEL)
+  int rsa_kernel = 0;                            // 0 auto, 28 force radix-2^28, 32 radix-2^32 without / 33 with the dedicated squaring (env BFTQ_RSA_KERNEL)
   std::vector<StagingSlot*> slots;
   bftq_stats_t stats{};
   std::map<std::string, uint32_t> key_lookup;   // (modulus bytes || e) -> key table index
@@ -384,26 +383,13 @@ int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_s
   const bool use32 = kb == 256 && (e->rsa_kernel == 32 || e->rsa_kernel == 33 || (e->rsa_kernel == 0 && e->all_2048));
   if (use32) {
     if (!e->all_2048) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a registered modulus is not 2048 bits");
-    if (e->rsa_kernel == 33) {                               // experimental squaring kernel (opt-in, see rsa_square_r32.cuh)
-      auto kern = bftq::r32::rsa_verify_r32sq_kernel<128, 4>;
-      const size_t smem = (size_t)bftq::r32::kSqWords * 128 * sizeof(uint32_t);
-      static thread_local int occsq = 0;
-      if (!occsq) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occsq, kern, 128, smem));
-        if (occsq < 1) occsq = 1;
-      }
-      const uint64_t per_block = 4 * 8;
-      uint64_t grid = std::min<uint64_t>((n_items + per_block - 1) / per_block, (uint64_t)e->sm_count * occsq);
-      if (grid < 1) grid = 1;
-      kern<<<(unsigned)grid, 128, smem, st>>>(e->d_keys32, (uint32_t)e->h_keys32.size(), d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
-                                              d_pre, d_status);
-      CU(cudaGetLastError());
-      return BFTQ_OK;
-    }
+    // rsa_kernel 32 = general products only (mont_mul(y, y)); default / 33 = the squarings go through mont_sqr
+    const bool sq = e->rsa_kernel != 32;
     static const int min_blocks = [] { const char* v = getenv("BFTQ_R32_BLOCKS"); return v ? atoi(v) : 4; }();
-    auto kern = min_blocks == 5 ? bftq::r32::rsa_verify_r32_kernel<128, 5> : (min_blocks == 3 ? bftq::r32::rsa_verify_r32_kernel<128, 3> : bftq::r32::rsa_verify_r32_kernel<128, 4>);
+    using kern_t = void (*)(const bftq::r32::RsaKey32*, uint32_t, const uint32_t*, const uint8_t*, const uint8_t*, uint32_t, uint64_t, uint32_t,
+                            const uint8_t*, uint8_t*);
+    kern_t kern = sq ? (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, true> : (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 4, true>)
+                     : (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, false> : (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 4, false>);
     static thread_local int occ32 = 0;
     if (!occ32) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, kern, 128, 0)); if (occ32 < 1) occ32 = 1; }
     const uint64_t per_block = 4 * 8;
@@ -475,7 +461,7 @@ int bftq_init(int device, bftq_engine** out) {
   if (const char* k = getenv("BFTQ_RSA_KERNEL")) {
     if (!strcmp(k, "r28")) e->rsa_kernel = 28;
     if (!strcmp(k, "r32")) e->rsa_kernel = 32;
-    if (!strcmp(k, "r32sq")) e->rsa_kernel = 33;       // experimental: radix 2^32 with the dedicated squaring (rsa_square_r32.cuh)
+    if (!strcmp(k, "r32sq")) e->rsa_kernel = 33;       // radix 2^32 with the dedicated squaring (the default for 2048-bit moduli)
   }
   if (const char* t = getenv("BFTQ_RSA_T")) {
     int v = atoi(t);

@@ -154,6 +154,52 @@ __device__ __forceinline__ uint32_t lane_carry_in(const uint32_t gbits, const ui
   return r == 0 ? 0u : (r == 1 ? c1 : (r == 2 ? c2 : c3));
 }
 
+// The tail of a Montgomery product: merges the E / O accumulators and the pending carries into W limbs per lane,
+// resolves the carries across the four lanes and subtracts n once when the result overflowed 2^(128 W).
+template <int W>
+__device__ __forceinline__ void mont_finish(uint32_t (&out)[W], Acc<W>& A, const uint32_t cin, const uint32_t Z, const uint32_t (&n)[W],
+                                            const int r, const int gbase) {
+  // ---- merge E, O and the pending carry into 16 limbs + overflow ------------------------------
+  uint32_t v[W], hi;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(v[0]) : "r"(A.E[0]), "r"(Z));
+#pragma unroll
+  for (int k = 1; k < W; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(v[k]) : "r"(A.E[k]), "r"(A.O[k - 1]));
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(hi) : "r"(A.E[W]), "r"(A.O[W - 1]));
+  // the lane's overflow (a few units) belongs to the lane above; the top lane's is bit 2048+
+  uint32_t from_below = __shfl_up_sync(kFull, hi, 1, T);
+  if (r == 0) from_below = 0u;
+  const uint32_t g = ripple_add(v, from_below + cin);
+  bool ones = true;
+#pragma unroll
+  for (int k = 0; k < W; k++) ones = ones && (v[k] == 0xffffffffu);
+  const uint32_t gb = __ballot_sync(kFull, g != 0u) >> gbase;
+  const uint32_t pb = __ballot_sync(kFull, ones) >> gbase;
+  uint32_t ctop;
+  const uint32_t ci = lane_carry_in(gb, pb, r, ctop);
+  ripple_add(v, ci);
+  const uint32_t top_hi = __shfl_sync(kFull, hi, gbase + T - 1);
+  const bool overflow = (top_hi + ctop) != 0u;          // result >= 2^2048: subtract n once
+  // ---- conditional subtraction ---------------------------------------------------------------
+  if (__any_sync(kFull, overflow)) {
+    uint32_t d[W];
+    const uint32_t bo = sub_n(d, v, n);
+    bool zeros = true;
+#pragma unroll
+    for (int k = 0; k < W; k++) zeros = zeros && (d[k] == 0u);
+    const uint32_t bgb = __ballot_sync(kFull, bo != 0u) >> gbase;
+    const uint32_t bpb = __ballot_sync(kFull, zeros) >> gbase;
+    uint32_t btop;
+    const uint32_t bi = lane_carry_in(bgb, bpb, r, btop);
+    ripple_sub(d, bi);
+    if (overflow) {
+#pragma unroll
+      for (int k = 0; k < W; k++) v[k] = d[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < W; k++) out[k] = v[k];
+}
+
 // out = a * b * R^-1 mod n with R = 2^(128 W), out < R ("almost Montgomery").  a, b < R as W limbs/lane.
 // All 32 lanes of the warp must call this together.
 template <int W>
@@ -209,45 +255,7 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
                    : "+r"(A.E[W - 2]), "+r"(A.E[W - 1]), "+r"(A.E[W]), "+r"(A.E[W + 1]) : "r"(r0), "r"(r1));
     }
   }
-  // ---- merge E, O and the pending carry into 16 limbs + overflow ------------------------------
-  uint32_t v[W], hi;
-  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(v[0]) : "r"(A.E[0]), "r"(Z));
-#pragma unroll
-  for (int k = 1; k < W; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(v[k]) : "r"(A.E[k]), "r"(A.O[k - 1]));
-  asm volatile("addc.u32 %0, %1, %2;" : "=r"(hi) : "r"(A.E[W]), "r"(A.O[W - 1]));
-  // the lane's overflow (a few units) belongs to the lane above; the top lane's is bit 2048+
-  uint32_t from_below = __shfl_up_sync(kFull, hi, 1, T);
-  if (r == 0) from_below = 0u;
-  const uint32_t g = ripple_add(v, from_below + cin);
-  bool ones = true;
-#pragma unroll
-  for (int k = 0; k < W; k++) ones = ones && (v[k] == 0xffffffffu);
-  const uint32_t gb = __ballot_sync(kFull, g != 0u) >> gbase;
-  const uint32_t pb = __ballot_sync(kFull, ones) >> gbase;
-  uint32_t ctop;
-  const uint32_t ci = lane_carry_in(gb, pb, r, ctop);
-  ripple_add(v, ci);
-  const uint32_t top_hi = __shfl_sync(kFull, hi, gbase + T - 1);
-  const bool overflow = (top_hi + ctop) != 0u;          // result >= 2^2048: subtract n once
-  // ---- conditional subtraction ---------------------------------------------------------------
-  if (__any_sync(kFull, overflow)) {
-    uint32_t d[W];
-    const uint32_t bo = sub_n(d, v, n);
-    bool zeros = true;
-#pragma unroll
-    for (int k = 0; k < W; k++) zeros = zeros && (d[k] == 0u);
-    const uint32_t bgb = __ballot_sync(kFull, bo != 0u) >> gbase;
-    const uint32_t bpb = __ballot_sync(kFull, zeros) >> gbase;
-    uint32_t btop;
-    const uint32_t bi = lane_carry_in(bgb, bpb, r, btop);
-    ripple_sub(d, bi);
-    if (overflow) {
-#pragma unroll
-      for (int k = 0; k < W; k++) v[k] = d[k];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < W; k++) out[k] = v[k];
+  mont_finish(out, A, cin, Z, n, r, gbase);
 }
 
 // x >= n ?  (lane-distributed compare)
@@ -284,6 +292,12 @@ __device__ __forceinline__ void cond_sub(uint32_t (&x)[W], const uint32_t (&n)[W
   }
 }
 
+}  // namespace r32
+}  // namespace bftq
+#include "rsa_square_r32.cuh"
+namespace bftq {
+namespace r32 {
+
 struct RsaKey32 {               // per key, radix 2^32 little-endian words
   uint32_t n[64];
   uint32_t r2[64];              // 2^4096 mod n
@@ -293,7 +307,8 @@ struct RsaKey32 {               // per key, radix 2^32 little-endian words
   uint32_t pad;
 };
 
-template <int BLOCK, int MIN_BLOCKS>
+// SQ: the squarings of the exponentiation go through mont_sqr (rsa_square_r32.cuh) instead of mont_mul(y, y).
+template <int BLOCK, int MIN_BLOCKS, bool SQ>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, const uint32_t* __restrict__ key_idx,
                       const uint8_t* __restrict__ sig, const uint8_t* __restrict__ digest, const uint32_t hash_alg,
@@ -347,7 +362,7 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
 #pragma unroll 1
     for (int bit = nbmax - 2; bit >= 1; bit--) {
       const bool active = bit <= nb - 2;
-      mont_mul(t, y, y, nd, n0inv, r, gbase);
+      if (SQ) mont_sqr(t, y, nd, n0inv, r, gbase); else mont_mul(t, y, y, nd, n0inv, r, gbase);
       if (active) {
 #pragma unroll
         for (int j = 0; j < W; j++) y[j] = t[j];
@@ -365,7 +380,7 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
       }
     }
     if (__any_sync(kFull, nb >= 2)) {
-      mont_mul(t, y, y, nd, n0inv, r, gbase);
+      if (SQ) mont_sqr(t, y, nd, n0inv, r, gbase); else mont_mul(t, y, y, nd, n0inv, r, gbase);
       if (nb >= 2) {
 #pragma unroll
         for (int j = 0; j < W; j++) y[j] = t[j];

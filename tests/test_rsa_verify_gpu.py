@@ -215,14 +215,14 @@ def test_roundtrip_property_fresh_keys(built):
     e.close()
 
 
-@pytest.mark.skipif(os.environ.get("BFTQ_TEST_R32SQ") != "1",
-                    reason="experimental squaring kernel (BFTQ_RSA_KERNEL=r32sq): opt in with BFTQ_TEST_R32SQ=1 until it has been validated on a GPU")
-def test_experimental_squaring_kernel_bit_exact(batch64k, built):
-    """rsa_square_r32.cuh (dedicated Montgomery squaring, emulated limb for limb by tools/emu_sq.py) against the
-    oracle on config 2, ragged sizes and the edge values of s."""
+@pytest.mark.parametrize("variant", ["r32", "r32sq"])
+def test_r32_kernel_variants_bit_exact(batch64k, built, variant):
+    """Both radix-2^32 kernels — squarings through mont_sqr (rsa_square_r32.cuh, the default; emulated limb for limb by
+    tools/emu_sq.py) and through the general product mont_mul(y, y) (BFTQ_RSA_KERNEL=r32) — against the oracle on
+    config 2, ragged sizes and the edge values of s."""
     w = batch64k
     ns, es = [k["n"] for k in w["keys"]], [k["e"] for k in w["keys"]]
-    os.environ["BFTQ_RSA_KERNEL"] = "r32sq"
+    os.environ["BFTQ_RSA_KERNEL"] = variant
     try:
         e = Engine(0)
     finally:
