@@ -51,7 +51,7 @@ template <int JJ>
 __device__ __forceinline__ void sqr_iter(Acc<16>& A, uint32_t& cin, uint32_t& Z, const uint32_t (&a2)[17], const uint32_t (&n)[16],
                                          const uint32_t n0inv, const int r, const int gbase, const int owner) {
   constexpr int W = 16;
-  const bool lt = r < owner, eq = r == owner;
+  const uint32_t lt1 = r < owner ? ~1u : 0u, nm = r < owner ? ~0u : ~1u, eqm = r == owner ? ~0u : 0u;
   // this lane's own limbs JJ and JJ + 1 (undoubled); the owner's are the round's multipliers
   const uint32_t aj0 = __funnelshift_r(a2[JJ], a2[JJ + 1], 1);
   const uint32_t aj1 = __funnelshift_r(a2[JJ + 1], a2[JJ + 2], 1);
@@ -62,12 +62,13 @@ __device__ __forceinline__ void sqr_iter(Acc<16>& A, uint32_t& cin, uint32_t& Z,
 #pragma unroll
   for (int k = 0; k < 17; k++) { m0[k] = a2[k]; m1[k] = a2[k]; }
   m0[17] = 0u; m1[17] = 0u;
-  m0[JJ] = lt ? (a2[JJ] & ~1u) : (eq ? aj0 : 0u);
-  m0[JJ + 1] = lt ? a2[JJ + 1] : (a2[JJ + 1] & ~1u);
-  m1[JJ + 1] = lt ? (a2[JJ + 1] & ~1u) : (eq ? aj1 : 0u);
+  // lt1 = lt ? ~1 : 0 (a doubled limb without the bit shifted in from the limb below), nm = lt ? ~0 : ~1, eqm = eq ? ~0 : 0
+  m0[JJ] = (a2[JJ] & lt1) | (aj0 & eqm);
+  m0[JJ + 1] = a2[JJ + 1] & nm;
+  m1[JJ + 1] = (a2[JJ + 1] & lt1) | (aj1 & eqm);
   uint32_t top1 = a2[16];
-  if (JJ + 2 < W) m1[JJ + 2] = lt ? a2[JJ + 2] : (a2[JJ + 2] & ~1u);
-  else top1 = lt ? a2[16] : 0u;                      // row 15: limb 15 is doubled only for the lanes below the owner
+  if (JJ + 2 < W) m1[JJ + 2] = a2[JJ + 2] & nm;
+  else top1 = a2[16] & (lt1 >> 1);                    // row 15: limb 15 is doubled only for the lanes below the owner
   const uint32_t t0 = (0u - a2[16]) & b0;            // a2[16] (0/1) x b: lands on the even chain's first carry limb
   const uint32_t t1 = (0u - top1) & b1;
   // ---- offset 0 ---------------------------------------------------------------------------------------------
@@ -118,7 +119,11 @@ __device__ __forceinline__ void mont_sqr(uint32_t (&out)[16], const uint32_t (&a
 #pragma unroll
   for (int k = 0; k < W + 2; k++) A.O[k] = 0u;
   uint32_t cin = 0u, Z = 0u;
-#pragma unroll 1
+#ifndef BFTQ_SQR_UNROLL
+#define BFTQ_SQR_UNROLL 1
+#endif
+  constexpr int kSqrUnroll = BFTQ_SQR_UNROLL;      // owner steps per loop body (code size x this)
+#pragma unroll kSqrUnroll
   for (int owner = 0; owner < T; owner++) {
     sqr_iter<0>(A, cin, Z, a2, n, n0inv, r, gbase, owner);
     sqr_iter<2>(A, cin, Z, a2, n, n0inv, r, gbase, owner);

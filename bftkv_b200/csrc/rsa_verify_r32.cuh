@@ -212,7 +212,11 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
   for (int k = 0; k < W + 2; k++) A.O[k] = 0u;
   uint32_t cin = 0u;      // 1-bit carry pending at position 0
   uint32_t Z = 0u;        // odd-side limb pending at position 0 (the upper half of the O pair the shift cut)
-#pragma unroll 1
+#ifndef BFTQ_MUL_UNROLL
+#define BFTQ_MUL_UNROLL 1
+#endif
+  constexpr int kMulUnroll = BFTQ_MUL_UNROLL;      // owner steps per loop body (code size x this)
+#pragma unroll kMulUnroll
   for (int owner = 0; owner < T; owner++) {
     const int src = gbase + owner;
 #pragma unroll

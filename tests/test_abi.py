@@ -44,3 +44,26 @@ def test_sass_is_carry_free_imad_wide(built):
         wide = len(re.findall(r"IMAD\.WIDE\.U32 ", b))
         widex = len(re.findall(r"IMAD\.WIDE\.U32\.X", b))
         assert wide > 100 and widex == 0, (wide, widex)
+
+
+def test_sass_r32_kernels_resource_guard(built):
+    """The radix-2^32 kernels every headline number comes from (rsa_verify_r32_kernel<128, 4, SQ>): carry-chained
+    IMAD.WIDE.U32.X products, 128 registers (4 blocks x 128 threads per SM), at most a few spilled words, and the
+    squaring variant carries FEWER wide multiplies in its exponentiation loop than the general-product one."""
+    import subprocess
+    so = os.path.join(ROOT, "bftkv_b200", "libbftq.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
+    seen = {}
+    for sq in ("Lb0", "Lb1"):
+        name = "rsa_verify_r32_kernelILi128ELi4E" + sq
+        blk = [b for b in sass.split("Function :") if name in b.split("\n")[0]]
+        assert len(blk) == 1, name
+        widex = len(re.findall(r"IMAD\.WIDE\.U32\.X", blk[0]))
+        assert widex > 1000, (name, widex)
+        m = re.search(r"Function [^\n]*" + name + r"[^\n]*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res)
+        assert m, name
+        regs, stack, shared, local = map(int, m.groups())
+        assert regs <= 128 and stack <= 64 and local == 0 and shared <= 16384, (name, regs, stack, shared, local)
+        seen[sq] = widex
+    assert seen["Lb1"] < seen["Lb0"]
