@@ -16,7 +16,8 @@ class BftqError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("items", C.c_uint64), ("launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("packer_chunks", C.c_uint64),
-                ("packer_parse_ns", C.c_uint64), ("packer_stage_ns", C.c_uint64), ("packer_wait_ns", C.c_uint64)]
+                ("packer_parse_ns", C.c_uint64), ("packer_stage_ns", C.c_uint64), ("packer_wait_ns", C.c_uint64),
+                ("numa_node", C.c_int32), ("numa_cpus", C.c_uint32)]
 
 
 _lib = None
@@ -38,6 +39,13 @@ def load():
         "bftq_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "bftq_shutdown": (None, [vp]),
         "bftq_device_sm_count": (C.c_int, [vp]),
+        "bftq_host_alloc": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
+        "bftq_host_free": (C.c_int, [vp, vp]),
+        "bftq_bind_thread": (C.c_int, [vp]),
+        "bftq_read_decide_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp]),
+        "bftq_verify_read_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp, vp, vp]),
+        "bftq_verify_read_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32,
+                                                 vp, vp, vp, vp, vp, vp]),
         "bftq_key_count": (C.c_int, [vp]),
         "bftq_register_rsa_keys": (C.c_int, [vp, vp, vp, C.c_uint32, u32p]),
         "bftq_register_rsa_keys_k": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, u32p]),
@@ -53,6 +61,7 @@ def load():
         "bftq_verify_tally_batch_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_uint64,
                                                   C.c_uint32, vp, vp, vp, vp]),
         "bftq_lagrange_combine_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, vp]),
+        "bftq_lagrange_combine_batch_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, vp, vp]),
         "bftq_ed25519_verify_batch": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),
         "bftq_ed25519_verify_batch_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp, vp]),
         "bftq_modprod_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]),

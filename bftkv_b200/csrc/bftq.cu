@@ -33,6 +33,9 @@
 #include <string>
 #include <vector>
 
+#include <sched.h>
+#include <unistd.h>
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -121,11 +124,13 @@ struct PackerPool {
   std::deque<std::shared_ptr<Job>> jobs;
   std::vector<std::thread> threads;
   bool stop = false;
+  std::function<void()> on_start;            // run once by every pool thread (NUMA binding to the engine's GPU)
 
   void ensure(unsigned n) {                  // grow to n threads (under mu)
     while (threads.size() < n) threads.emplace_back([this] { loop(); });
   }
   void loop() {
+    if (on_start) on_start();
     std::unique_lock<std::mutex> l(mu);
     for (;;) {
       std::shared_ptr<Job> j;
@@ -185,11 +190,61 @@ struct bftq_engine {
   std::vector<DsaKey> dsa_keys;                  // host table; a group's domain travels with its launch
   std::map<std::string, uint32_t> dsa_lookup;
   PackerPool pool;                               // host workers of the packet-level entry points
+  // NUMA placement: the CPUs of the node the GPU hangs off (intersected with the process's affinity mask).  The pool's
+  // threads are bound to them and pinned staging memory is allocated from a thread bound to them, so that staging
+  // copies and the DMA engine read node-local memory (8-GPU boxes: GPUs 4-7 sit on the second socket).
+  int numa_node = -1;
+  bool numa_valid = false;
+  cpu_set_t numa_cpus;
+  std::map<void*, size_t> host_allocs;           // bftq_host_alloc blocks
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
 
 namespace {
+
+void numa_probe(bftq_engine* e) {
+  e->numa_valid = false;
+  if (const char* v = getenv("BFTQ_NUMA_BIND")) if (atoi(v) == 0) return;
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), e->device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char* c = bdf; *c; c++) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+  int node = -1;
+  if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  e->numa_node = node;
+  if (node < 0) return;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  char list[4096] = {0};
+  const size_t got = fread(list, 1, sizeof(list) - 1, f);
+  fclose(f);
+  list[got] = 0;
+  cpu_set_t node_cpus, mine;
+  CPU_ZERO(&node_cpus);
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &node_cpus);
+  }
+  if (sched_getaffinity(0, sizeof(mine), &mine) != 0) return;
+  CPU_AND(&e->numa_cpus, &node_cpus, &mine);
+  e->numa_valid = CPU_COUNT(&e->numa_cpus) > 0 && CPU_COUNT(&e->numa_cpus) < CPU_COUNT(&mine);   // nothing to gain when the mask is the node already
+}
+void numa_bind_this_thread(bftq_engine* e) {
+  if (e && e->numa_valid) sched_setaffinity(0, sizeof(e->numa_cpus), &e->numa_cpus);
+}
+// Runs the enclosing scope on the GPU's NUMA node (page-locked allocations land where the allocating thread runs).
+struct ScopedNumaBind {
+  cpu_set_t saved; bool active = false;
+  explicit ScopedNumaBind(bftq_engine* e) {
+    if (e && e->numa_valid && sched_getaffinity(0, sizeof(saved), &saved) == 0) { active = sched_setaffinity(0, sizeof(e->numa_cpus), &e->numa_cpus) == 0; }
+  }
+  ~ScopedNumaBind() { if (active) sched_setaffinity(0, sizeof(saved), &saved); }
+};
 
 // Picks a free staging slot: the smallest one that is already large enough, else the largest free one
 // (which then grows), else a new one.  Growing means cudaFreeHost / cudaHostAlloc / cudaMalloc — calls that
@@ -217,6 +272,7 @@ int acquire_slot(bftq_engine* e, size_t h_bytes, size_t d_bytes, StagingSlot** o
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     s->h_pinned = nullptr; s->h_cap = 0;
     const size_t cap = round_up(h_bytes);
+    ScopedNumaBind on_node(e);
     CU(cudaHostAlloc((void**)&s->h_pinned, cap, cudaHostAllocDefault));
     s->h_cap = cap;
   }
@@ -467,13 +523,49 @@ int bftq_init(int device, bftq_engine** out) {
     int v = atoi(t);
     if (v == 4 || v == 8) e->rsa_t = v;
   }
+  numa_probe(e);
+  e->pool.on_start = [e] { numa_bind_this_thread(e); };
   *out = e;
   return BFTQ_OK;
+}
+
+int bftq_host_alloc(bftq_engine* e, uint64_t bytes, void** out) {
+  if (!e || !out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  CU(cudaSetDevice(e->device));
+  void* p = nullptr;
+  {
+    ScopedNumaBind on_node(e);
+    CU(cudaHostAlloc(&p, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocPortable));
+  }
+  std::lock_guard<std::mutex> g(e->mu);
+  e->host_allocs[p] = (size_t)bytes;
+  *out = p;
+  return BFTQ_OK;
+}
+int bftq_host_free(bftq_engine* e, void* p) {
+  if (!e) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!p) return BFTQ_OK;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    auto it = e->host_allocs.find(p);
+    if (it == e->host_allocs.end()) return fail(BFTQ_ERR_INVALID_ARG, "not a bftq_host_alloc block of this engine");
+    e->host_allocs.erase(it);
+  }
+  CU(cudaSetDevice(e->device));
+  CU(cudaFreeHost(p));
+  return BFTQ_OK;
+}
+int bftq_bind_thread(bftq_engine* e) {
+  if (!e) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  numa_bind_this_thread(e);
+  return e->numa_valid ? e->numa_node : -1;
 }
 
 void bftq_shutdown(bftq_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  for (auto& kv : e->host_allocs) cudaFreeHost(kv.first);
   for (auto* s : e->slots) {
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->done) cudaEventDestroy(s->done);
@@ -738,12 +830,13 @@ struct bftq_quorum {
 
 namespace {
 int launch_tally(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_off, const uint32_t* d_idx, const uint8_t* d_status,
-                 const uint64_t* d_ts, const uint32_t* d_val, uint64_t n_ops, uint32_t* d_winner, uint8_t* d_bits, cudaStream_t st) {
+                 const uint64_t* d_ts, const uint32_t* d_val, uint64_t n_ops, uint32_t* d_winner, uint8_t* d_bits, cudaStream_t st,
+                 uint8_t* d_decision = nullptr, uint32_t* d_decided_at = nullptr) {
   const int block = 256, wpb = block / 32;
   uint64_t grid = std::min<uint64_t>((n_ops + wpb - 1) / wpb, (uint64_t)e->sm_count * 8);
   if (grid < 1) grid = 1;
   if (d_ts && d_val)
-    bftq::read_tally_kernel<<<(unsigned)grid, block, 0, st>>>(q->dev, d_off, d_idx, d_status, d_ts, d_val, n_ops, d_winner, d_bits);
+    bftq::read_tally_kernel<<<(unsigned)grid, block, 0, st>>>(q->dev, d_off, d_idx, d_status, d_ts, d_val, n_ops, d_winner, d_bits, d_decision, d_decided_at);
   else
     bftq::tally_kernel<<<(unsigned)grid, block, 0, st>>>(q->dev, d_off, d_idx, d_status, n_ops, d_bits);
   CU(cudaGetLastError());
@@ -796,7 +889,8 @@ void bftq_quorum_destroy(bftq_engine* e, bftq_quorum* q) {
 }
 
 static int tally_host(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx, const uint8_t* status,
-                      const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t* out_winner, uint8_t* out_bits) {
+                      const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t* out_winner, uint8_t* out_bits,
+                      uint8_t* out_decision = nullptr, uint32_t* out_decided_at = nullptr) {
   if (!e || !q || !op_off || !out_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (n_ops == 0) return BFTQ_OK;
   const uint64_t n_items = op_off[n_ops];
@@ -805,7 +899,7 @@ static int tally_host(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_o
     for (uint64_t i = 0; i < n_ops; i++)
       if (op_off[i + 1] - op_off[i] > 32) return fail(BFTQ_ERR_INVALID_ARG, "read tally: more than 32 responders in one operation");
   Arena a(e);
-  uint32_t *d_off, *d_idx, *d_val = nullptr, *d_win = nullptr; uint8_t *d_st, *d_bits; uint64_t* d_ts = nullptr;
+  uint32_t *d_off, *d_idx, *d_val = nullptr, *d_win = nullptr, *d_at = nullptr; uint8_t *d_st, *d_bits, *d_dec = nullptr; uint64_t* d_ts = nullptr;
   a.in(&d_off, op_off, (size_t)n_ops + 1);
   a.in(&d_idx, key_idx, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
   a.in(&d_st, status, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
@@ -813,11 +907,12 @@ static int tally_host(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_o
     a.in(&d_ts, ts, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
     a.in(&d_val, value_id, (size_t)std::max<uint64_t>(n_items, 1), (size_t)n_items);
     a.out(&d_win, out_winner, (size_t)n_ops);
+    if (out_decision) { a.out(&d_dec, out_decision, (size_t)n_ops); a.out(&d_at, out_decided_at, (size_t)n_ops); }
   }
   a.out(&d_bits, out_bits, (size_t)n_ops);
   int rc = a.upload();
   if (rc) return rc;
-  rc = launch_tally(e, q, d_off, d_idx, d_st, d_ts, d_val, n_ops, d_win, d_bits, a.stream());
+  rc = launch_tally(e, q, d_off, d_idx, d_st, d_ts, d_val, n_ops, d_win, d_bits, a.stream(), d_dec, d_at);
   if (rc) return rc;
   return a.download();
 }
@@ -834,28 +929,58 @@ int bftq_read_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* 
   return tally_host(e, q, op_off, key_idx, status, ts, value_id, n_ops, out_winner, out_bits);
 }
 
-int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
-                                const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg,
-                                const uint8_t* d_pre_status, const uint64_t* d_ts, const uint32_t* d_value_id,
-                                uint64_t n_ops, uint64_t n_items, uint32_t flags, uint8_t* d_status, uint8_t* d_bits,
-                                uint32_t* d_winner, void* cuda_stream) {
+int bftq_read_decide_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                           const uint8_t* status, const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops,
+                           uint8_t* out_decision, uint32_t* out_winner, uint32_t* out_decided_at) {
+  if (!ts || !value_id || !out_winner || !out_decision || !out_decided_at) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<uint8_t> bits((size_t)std::max<uint64_t>(n_ops, 1));
+  return tally_host(e, q, op_off, key_idx, status, ts, value_id, n_ops, out_winner, bits.data(), out_decision, out_decided_at);
+}
+
+static int verify_tally_dev_impl(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                                 const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg, const uint8_t* d_pre_status,
+                                 const uint64_t* d_ts, const uint32_t* d_value_id, uint64_t n_ops, uint64_t n_items, uint32_t flags,
+                                 uint8_t* d_status, uint8_t* d_bits, uint32_t* d_winner, uint8_t* d_decision, uint32_t* d_decided_at,
+                                 cudaStream_t st) {
   if (!e || !q || !d_op_off || !d_status || !d_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (bftq::host_hash_dlen(hash_alg) == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_ops == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
   if (n_items) {
     if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
     int rc = launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_pre_status, d_status, st);
     if (rc) return rc;
   }
-  return launch_tally(e, q, d_op_off, d_key_idx, d_status, d_ts, d_value_id, n_ops, d_winner, d_bits, st);
+  return launch_tally(e, q, d_op_off, d_key_idx, d_status, d_ts, d_value_id, n_ops, d_winner, d_bits, st, d_decision, d_decided_at);
 }
 
-int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
-                            const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
-                            const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
-                            uint8_t* out_status, uint8_t* out_bits, uint32_t* out_winner) {
+int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                                const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg,
+                                const uint8_t* d_pre_status, const uint64_t* d_ts, const uint32_t* d_value_id,
+                                uint64_t n_ops, uint64_t n_items, uint32_t flags, uint8_t* d_status, uint8_t* d_bits,
+                                uint32_t* d_winner, void* cuda_stream) {
+  return verify_tally_dev_impl(e, q, d_op_off, d_key_idx, d_sig_be, d_digest, hash_alg, d_pre_status, d_ts, d_value_id, n_ops, n_items, flags,
+                               d_status, d_bits, d_winner, nullptr, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int bftq_verify_read_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                               const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg, const uint8_t* d_pre_status,
+                               const uint64_t* d_ts, const uint32_t* d_value_id, uint64_t n_ops, uint64_t n_items, uint32_t flags,
+                               uint8_t* d_status, uint8_t* d_bits, uint8_t* d_decision, uint32_t* d_winner, uint32_t* d_decided_at,
+                               void* cuda_stream) {
+  if (!d_ts || !d_value_id || !d_decision || !d_winner || !d_decided_at) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  return verify_tally_dev_impl(e, q, d_op_off, d_key_idx, d_sig_be, d_digest, hash_alg, d_pre_status, d_ts, d_value_id, n_ops, n_items, flags,
+                               d_status, d_bits, d_winner, d_decision, d_decided_at, (cudaStream_t)cuda_stream);
+}
+
+// Host form of the fused verify + tally calls.  The operations are cut into chunks of whole operations (about
+// BFTQ_HOST_CHUNK tuples each) that travel through a ring of four staging slots, one stream each: the copies of chunk
+// c + 1 run under the kernels of chunk c, pinned caller memory (bftq_host_alloc) is DMA'd in place, pageable memory is
+// bounced through the slot's pinned mirror.  The offsets are rebased per chunk in staging.
+static int verify_tally_host(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx, const uint8_t* sig_be,
+                             const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status, const uint64_t* ts, const uint32_t* value_id,
+                             uint64_t n_ops, uint32_t flags, uint8_t* out_status, uint8_t* out_bits, uint32_t* out_winner,
+                             uint8_t* out_decision, uint32_t* out_decided_at) {
   if (!e || !q || !op_off || !out_status || !out_bits) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   const int dlen = bftq::host_hash_dlen(hash_alg);
   if (dlen == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
@@ -863,28 +988,75 @@ int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t
   const uint64_t n_items = op_off[n_ops];
   if (n_items && (!key_idx || !sig_be || !digest)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   const bool read = ts && value_id;
-  if (read) {
-    if (!out_winner) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
-    for (uint64_t i = 0; i < n_ops; i++)
-      if (op_off[i + 1] - op_off[i] > 32) return fail(BFTQ_ERR_INVALID_ARG, "read tally: more than 32 responders in one operation");
+  if (read && !out_winner) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (out_decision && (!read || !out_decided_at)) return fail(BFTQ_ERR_INVALID_ARG, "the read decision needs ts, value_id and out_decided_at");
+  for (uint64_t i = 0; i < n_ops; i++) {
+    if (op_off[i + 1] < op_off[i]) return fail(BFTQ_ERR_INVALID_ARG, "op_off must be non-decreasing");
+    if (read && op_off[i + 1] - op_off[i] > 32) return fail(BFTQ_ERR_INVALID_ARG, "read tally: more than 32 responders in one operation");
   }
-  const size_t ni = (size_t)std::max<uint64_t>(n_items, 1);
-  Arena a(e);
-  uint32_t *d_off, *d_idx, *d_val = nullptr, *d_win = nullptr; uint8_t *d_sig, *d_dig, *d_pre = nullptr, *d_st, *d_bits; uint64_t* d_ts = nullptr;
-  a.in(&d_sig, sig_be, ni * 256, (size_t)n_items * 256);
-  a.in(&d_dig, digest, ni * dlen, (size_t)n_items * dlen);
-  a.in(&d_off, op_off, (size_t)n_ops + 1);
-  a.in(&d_idx, key_idx, ni, (size_t)n_items);
-  if (pre_status) a.in(&d_pre, pre_status, ni, (size_t)n_items);
-  if (read) { a.in(&d_ts, ts, ni, (size_t)n_items); a.in(&d_val, value_id, ni, (size_t)n_items); a.out(&d_win, out_winner, (size_t)n_ops); }
-  a.out(&d_st, out_status, ni, (size_t)n_items);
-  a.out(&d_bits, out_bits, (size_t)n_ops);
-  int rc = a.upload();
-  if (rc) return rc;
-  rc = bftq_verify_tally_batch_dev(e, q, d_off, d_idx, d_sig, d_dig, hash_alg, d_pre, d_ts, d_val, n_ops, n_items, flags, d_st, d_bits,
-                                   d_win, a.stream());
-  if (rc) return rc;
-  return a.download();
+  static const uint64_t kChunk = [] { const char* v = getenv("BFTQ_HOST_CHUNK"); const long long c = v ? atoll(v) : 16384; return (uint64_t)(c > 0 ? c : 16384); }();
+  constexpr int kDepth = 4;
+  std::unique_ptr<Arena> ring[kDepth];
+  int rc = BFTQ_OK;
+  uint64_t lo = 0, c = 0;
+  while (lo < n_ops && rc == BFTQ_OK) {
+    // chunk [lo, hi): whole operations, about kChunk tuples (at least one operation)
+    uint64_t hi = lo + 1;
+    if (n_items <= kChunk + kChunk / 2) hi = n_ops;
+    else {
+      const uint32_t want = op_off[lo] + (uint32_t)std::min<uint64_t>(kChunk, 0xffffffffu - op_off[lo]);
+      hi = (uint64_t)(std::upper_bound(op_off + lo + 1, op_off + n_ops + 1, want) - op_off) - 1;
+      if (hi <= lo) hi = lo + 1;
+      if (n_items - op_off[hi] < kChunk / 2) hi = n_ops;                  // do not leave a sliver behind
+    }
+    const uint64_t t0 = op_off[lo], cnt = op_off[hi] - t0, nops = hi - lo;
+    const size_t ni = (size_t)std::max<uint64_t>(cnt, 1);
+    std::unique_ptr<Arena>& slot = ring[c % kDepth];
+    if (slot) { rc = slot->finish(); slot.reset(); if (rc) break; }
+    slot.reset(new Arena(e));
+    Arena& a = *slot;
+    uint32_t *d_off, *h_off, *d_idx, *d_val = nullptr, *d_win = nullptr, *d_at = nullptr;
+    uint8_t *d_sig, *d_dig, *d_pre = nullptr, *d_st, *d_bits, *d_dec = nullptr; uint64_t* d_ts = nullptr;
+    a.in(&d_sig, sig_be + t0 * 256, ni * 256, (size_t)cnt * 256);
+    a.in(&d_dig, digest + t0 * dlen, ni * dlen, (size_t)cnt * dlen);
+    a.in(&d_idx, key_idx + t0, ni, (size_t)cnt);
+    if (pre_status) a.in(&d_pre, pre_status + t0, ni, (size_t)cnt);
+    if (read) { a.in(&d_ts, ts + t0, ni, (size_t)cnt); a.in(&d_val, value_id + t0, ni, (size_t)cnt); a.out(&d_win, out_winner + lo, (size_t)nops); }
+    if (out_decision) { a.out(&d_dec, out_decision + lo, (size_t)nops); a.out(&d_at, out_decided_at + lo, (size_t)nops); }
+    a.stage(&d_off, &h_off, (size_t)nops + 1);
+    a.out(&d_st, out_status + t0, ni, (size_t)cnt);
+    a.out(&d_bits, out_bits + lo, (size_t)nops);
+    rc = a.prepare();
+    if (rc) break;
+    for (uint64_t i = 0; i <= nops; i++) h_off[i] = op_off[lo + i] - (uint32_t)t0;
+    rc = a.upload();
+    if (rc) break;
+    rc = verify_tally_dev_impl(e, q, d_off, d_idx, d_sig, d_dig, hash_alg, d_pre, d_ts, d_val, nops, cnt, flags, d_st, d_bits, d_win, d_dec, d_at,
+                               a.stream());
+    if (rc) break;
+    rc = a.download_async();
+    lo = hi; c++;
+  }
+  for (auto& slot : ring) if (slot) { const int r2 = slot->finish(); if (!rc) rc = r2; slot.reset(); }
+  return rc;
+}
+
+int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                            const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
+                            const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
+                            uint8_t* out_status, uint8_t* out_bits, uint32_t* out_winner) {
+  return verify_tally_host(e, q, op_off, key_idx, sig_be, digest, hash_alg, pre_status, ts, value_id, n_ops, flags, out_status, out_bits, out_winner,
+                           nullptr, nullptr);
+}
+
+int bftq_verify_read_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx, const uint8_t* sig_be,
+                           const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status, const uint64_t* ts, const uint32_t* value_id,
+                           uint64_t n_ops, uint32_t flags, uint8_t* out_status, uint8_t* out_decision, uint32_t* out_winner,
+                           uint32_t* out_decided_at) {
+  if (!out_decision || !out_winner || !out_decided_at || !ts || !value_id) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::vector<uint8_t> bits((size_t)std::max<uint64_t>(n_ops, 1));
+  return verify_tally_host(e, q, op_off, key_idx, sig_be, digest, hash_alg, pre_status, ts, value_id, n_ops, flags, out_status, bits.data(), out_winner,
+                           out_decision, out_decided_at);
 }
 
 // ---- K3 ---------------------------------------------------------------------------------------
@@ -1035,6 +1207,17 @@ int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t ml
   rc = launch_lagrange_any(e, m_be, mlen, k, d_x, d_y, n_items, d_out, d_st, nullptr, a.stream());
   if (rc) return rc;
   return a.download();
+}
+
+int bftq_lagrange_combine_batch_dev(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* d_x, const uint8_t* d_y_be,
+                                    uint64_t n_items, uint8_t* d_out_be, uint8_t* d_status, void* cuda_stream) {
+  if (!e || !m_be || !d_x || !d_y_be || !d_out_be || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || k > 255) return fail(BFTQ_ERR_INVALID_ARG, "k must be 1..255");
+  int rc = check_modulus(m_be, mlen);
+  if (rc) return rc;
+  if (n_items == 0) return BFTQ_OK;
+  CU(cudaSetDevice(e->device));
+  return launch_lagrange_any(e, m_be, mlen, k, d_x, d_y_be, n_items, d_out_be, d_status, nullptr, (cudaStream_t)cuda_stream);
 }
 
 // ---- K5 ---------------------------------------------------------------------------------------
@@ -1354,6 +1537,8 @@ int bftq_stats(bftq_engine* e, bftq_stats_t* out) {
   if (!e || !out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::lock_guard<std::mutex> g(e->mu);
   *out = e->stats;
+  out->numa_node = e->numa_node;
+  out->numa_cpus = e->numa_valid ? (uint32_t)CPU_COUNT(&e->numa_cpus) : 0u;
   return BFTQ_OK;
 }
 

@@ -45,8 +45,8 @@ struct FastSrc {
 };
 
 __global__ void __launch_bounds__(128)
-pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __restrict__ tbs_off,
-                        const uint8_t* __restrict__ sig_blob, const uint64_t* __restrict__ sig_off, const uint32_t n_items,
+pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __restrict__ tbs_off, const uint64_t tbs_base,
+                        const uint8_t* __restrict__ sig_blob, const uint64_t* __restrict__ sig_off, const uint64_t sig_base, const uint32_t n_items,
                         const IssuerEntry* __restrict__ issuers, const uint32_t n_issuers,
                         uint32_t* __restrict__ out_key_idx, uint8_t* __restrict__ out_sig /* n x 256 */,
                         uint8_t* __restrict__ out_digest /* n x 32 */, uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where) {
@@ -54,7 +54,8 @@ pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __
   const bool live = item_raw < n_items;
   const uint32_t item = live ? item_raw : n_items - 1;        // idle lanes shadow the last item (the warp copies together)
   const int lane = threadIdx.x & 31;
-  const uint64_t s0 = tbs_off[item], s1 = tbs_off[item + 1], g0 = sig_off[item], g1 = sig_off[item + 1];
+  // offsets are the caller's own (relative to its whole blob): the chunk's blobs start at tbs_base / sig_base
+  const uint64_t s0 = tbs_off[item] - tbs_base, s1 = tbs_off[item + 1] - tbs_base, g0 = sig_off[item] - sig_base, g1 = sig_off[item + 1] - sig_base;
   const uint8_t* sg = sig_blob + g0;
   // ---- per item: parse, issuer lookup ---------------------------------------------------------------
   uint8_t where = kParseDecided, pre = 0;

@@ -82,7 +82,8 @@ tally_kernel(const QuorumDev q, const uint32_t* __restrict__ op_off, const uint3
 __global__ void __launch_bounds__(256)
 read_tally_kernel(const QuorumDev q, const uint32_t* __restrict__ op_off, const uint32_t* __restrict__ key_idx,
                   const uint8_t* __restrict__ status, const uint64_t* __restrict__ ts, const uint32_t* __restrict__ value_id,
-                  const uint64_t n_ops, uint32_t* __restrict__ out_winner, uint8_t* __restrict__ out_bits) {
+                  const uint64_t n_ops, uint32_t* __restrict__ out_winner, uint8_t* __restrict__ out_bits,
+                  uint8_t* __restrict__ out_decision, uint32_t* __restrict__ out_decided_at) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
@@ -117,6 +118,51 @@ read_tally_kernel(const QuorumDev q, const uint32_t* __restrict__ op_off, const 
       }
     }
     const uint32_t winners = __ballot_sync(0xffffffffu, pass);
+    if (out_decision != nullptr) {
+      // ---- Client.Read's decision in ARRIVAL order (protocol/client.go:250-268): the multicast callback runs once per
+      // response; a good one is bucketed and maxTimestampedValue asked, a failed one joins `failure` and q.Reject is
+      // asked, and the first decisive response fixes the result.  Only the bucket the newest response joined can have
+      // become decisive (the others were inspected before, under the same or a smaller max t), so every lane j can
+      // judge "would the callback decide at response j" on its own from the responses 0..j:
+      //   value   : ok_j, t_j is the max t of the good responses 0..j, and the bucket (t_j, v_j) among 0..j passes IsThreshold
+      //   reject  : response j failed and the failed responses 0..j pass Reject
+      const uint32_t upto = 0xffffffffu >> (31 - lane);                      // lanes 0..lane
+      uint64_t pmax = t;                                                      // inclusive prefix maximum of t over the good lanes (t = 0 elsewhere)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t other = __shfl_up_sync(0xffffffffu, pmax, o);
+        if (lane >= o && other > pmax) pmax = other;
+      }
+      const uint32_t same_t = __match_any_sync(0xffffffffu, t);
+      const uint32_t same_v = __match_any_sync(0xffffffffu, v);
+      const uint32_t bucket = same_t & same_v & okmask & upto;                // responses 0..j in the bucket of response j
+      bool dv = ok && t == pmax && q.nqc > 0, dr = have && !ok;
+#pragma unroll
+      for (int c = 0; c < kMaxQc; c++) {
+        if (c < q.nqc) {
+          const uint32_t mm = __ballot_sync(0xffffffffu, have && is_member(q, c, k));
+          if (q.threshold[c] > 0 && __popc(bucket & mm) < q.threshold[c]) dv = false;
+          const int bad = __popc(mm & ~okmask & upto);
+          if (q.f[c] == 0 || bad <= q.f[c]) dr = false;
+        }
+      }
+      const uint32_t dvm = __ballot_sync(0xffffffffu, dv), drm = __ballot_sync(0xffffffffu, dr);
+      const uint32_t any = dvm | drm;
+      const int d = any ? __ffs(any) - 1 : 0;
+      const uint32_t bucket_d = __shfl_sync(0xffffffffu, bucket, d);
+      if (lane == 0) {
+        uint8_t dec = 2; uint32_t w = 0xffffffffu, at = hi - lo;
+        if (any) {
+          at = (uint32_t)d + 1;
+          if ((dvm >> d) & 1u) { dec = 0; w = (uint32_t)(__ffs(bucket_d) - 1); } else dec = 1;
+        }
+        out_decision[op] = dec;
+        out_decided_at[op] = at;
+        out_winner[op] = w;
+        out_bits[op] = (uint8_t)((winners != 0u && okmask != 0u ? 2 : 0) | (rej_all ? 8 : 0));
+      }
+      continue;
+    }
     if (lane == 0) {
       uint32_t w = 0xffffffffu;
       if (okmask != 0u && winners != 0u) {

@@ -17,6 +17,7 @@ class QC(C.Structure):
 
 TALLY_IS_QUORUM, TALLY_IS_THRESHOLD, TALLY_IS_SUFFICIENT, TALLY_REJECT = 1, 2, 4, 8
 NO_WINNER = 0xFFFFFFFF
+READ_VALUE, READ_REJECTED, READ_EXHAUSTED = 0, 1, 2
 
 
 def _ptr(a):
@@ -134,6 +135,63 @@ class Engine:
         _lib.check(self._lib.bftq_verify_tally_batch_dev(self._h, q, _ptr(d_op_off), _ptr(d_key_idx), _ptr(d_sig), _ptr(d_digest),
                                                          hash_alg, _ptr(d_pre), _ptr(d_ts), _ptr(d_value_id), n_ops, n_items, flags,
                                                          _ptr(d_status), _ptr(d_bits), _ptr(d_winner), C.c_void_p(stream)))
+
+    def read_decide_batch(self, q, op_off, key_idx, status, ts, value_id):
+        """Client.Read's decision per operation, responders in arrival order -> (decision, winner, decided_at)."""
+        n_ops = int(op_off.shape[0]) - 1
+        dec, win, at = np.empty(n_ops, np.uint8), np.empty(n_ops, np.uint32), np.empty(n_ops, np.uint32)
+        _lib.check(self._lib.bftq_read_decide_batch(self._h, q, _ptr(op_off), _ptr(key_idx), _ptr(status), _ptr(ts), _ptr(value_id), n_ops,
+                                                    _ptr(dec), _ptr(win), _ptr(at)))
+        return dec, win, at
+
+    def verify_read_batch(self, q, op_off, key_idx, sig_be, digest, ts, value_id, pre_status=None, hash_alg=HASH_SHA256, flags=0,
+                          out_status=None, out_decision=None, out_winner=None, out_decided_at=None):
+        """K1 + Client.Read's decision, host buffers of any size (chunked inside the library).
+        Returns (status, decision, winner, decided_at)."""
+        n_ops = int(op_off.shape[0]) - 1
+        n_items = int(key_idx.shape[0])
+        st = out_status if out_status is not None else np.empty(max(n_items, 1), np.uint8)
+        dec = out_decision if out_decision is not None else np.empty(n_ops, np.uint8)
+        win = out_winner if out_winner is not None else np.empty(n_ops, np.uint32)
+        at = out_decided_at if out_decided_at is not None else np.empty(n_ops, np.uint32)
+        _lib.check(self._lib.bftq_verify_read_batch(self._h, q, _ptr(op_off), _ptr(key_idx), _ptr(sig_be), _ptr(digest), hash_alg,
+                                                    _ptr(pre_status), _ptr(ts), _ptr(value_id), n_ops, flags, _ptr(st), _ptr(dec), _ptr(win),
+                                                    _ptr(at)))
+        return (st[:n_items] if out_status is None else st), dec, win, at
+
+    def verify_read_batch_dev(self, q, d_op_off, d_key_idx, d_sig, d_digest, d_ts, d_value_id, n_ops, n_items, d_status, d_bits, d_decision,
+                              d_winner, d_decided_at, d_pre=None, hash_alg=HASH_SHA256, flags=0, stream=0):
+        _lib.check(self._lib.bftq_verify_read_batch_dev(self._h, q, _ptr(d_op_off), _ptr(d_key_idx), _ptr(d_sig), _ptr(d_digest), hash_alg,
+                                                        _ptr(d_pre), _ptr(d_ts), _ptr(d_value_id), n_ops, n_items, flags, _ptr(d_status),
+                                                        _ptr(d_bits), _ptr(d_decision), _ptr(d_winner), _ptr(d_decided_at), C.c_void_p(stream)))
+
+    # ---- page-locked host memory on the GPU's NUMA node ----
+    def host_alloc(self, shape, dtype=np.uint8):
+        """numpy array over a bftq_host_alloc block (DMA'd in place by the *_batch calls).  Free with host_free(arr)."""
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(self._lib.bftq_host_alloc(self._h, max(nbytes, 1), C.byref(p)))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+        self._host_blocks = getattr(self, "_host_blocks", {})
+        self._host_blocks[arr.ctypes.data] = p.value
+        return arr
+
+    def host_copy(self, a):
+        """A page-locked copy of array `a` (what the shim does when it appends a request to its blob)."""
+        a = np.ascontiguousarray(a)
+        out = self.host_alloc(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def host_free(self, arr):
+        p = getattr(self, "_host_blocks", {}).pop(arr.ctypes.data, None)
+        if p is not None:
+            _lib.check(self._lib.bftq_host_free(self._h, C.c_void_p(p)))
+
+    def bind_thread(self) -> int:
+        return self._lib.bftq_bind_thread(self._h)
 
     # ---- K3 ----
     def lagrange_combine_batch(self, m: int, x, y_be):
@@ -266,7 +324,7 @@ class Engine:
         _lib.check(self._lib.bftq_stats(self._h, C.byref(s)))
         return {"items": s.items, "launches": s.launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes,
                 "packer_chunks": s.packer_chunks, "packer_parse_ns": s.packer_parse_ns, "packer_stage_ns": s.packer_stage_ns,
-                "packer_wait_ns": s.packer_wait_ns}
+                "packer_wait_ns": s.packer_wait_ns, "numa_node": s.numa_node, "numa_cpus": s.numa_cpus}
 
     def measure_int_peak(self) -> float:
         v = C.c_double()

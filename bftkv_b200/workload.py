@@ -86,27 +86,46 @@ def em_for_digest(digest: bytes) -> int:
     return int.from_bytes(b"\x00\x01" + b"\xff" * 202 + b"\x00" + SHA256_PREFIX + digest, "big")
 
 
-def make_read_ops(pool, n_ops: int, n_replicas: int, seed: int = 0xBF7C0004, p_ok=0.90, p_stale=0.05, p_bad=0.03):
+# Per-operation response mixes for make_read_ops: (share of the operations, p_ok, p_stale, p_bad); the rest of each
+# operation's replicas do not answer.  HARD_MIX makes a visible part of the operations end rejected or undecided, and
+# some decide on the stale value, so that every arm of Client.Read's decision is exercised at scale.
+HARD_MIX = [(0.80, 0.90, 0.05, 0.03), (0.08, 0.35, 0.30, 0.15), (0.07, 0.25, 0.05, 0.45), (0.05, 0.15, 0.60, 0.10)]
+
+
+def make_read_ops(pool, n_ops: int, n_replicas: int, seed: int = 0xBF7C0004, p_ok=0.90, p_stale=0.05, p_bad=0.03, mix=None,
+                  shuffle_arrival=False):
     """Configs 3 / 5: M read ops x R replicas.  Replica r of every op answers with key r.  Each
     response is (valid, current value) w.p. p_ok, (valid, stale t) p_stale, invalid signature p_bad,
     missing otherwise.  Signed tuples are drawn from `pool` (make_verify_batch output
     with n_keys == n_replicas, no corruption): slot (op, r) takes a pool item signed by key r, so
     every signature is genuine; uniqueness across ops is limited by the pool size (stated in
-    bench.py's `data`).  Returns op_off, key_idx, sig, digest, pre_status, ts, value_id and the
-    expected per-item status."""
+    bench.py's `data`).  mix: per-operation classes [(share, p_ok, p_stale, p_bad), ...] instead of one
+    global triple (HARD_MIX).  shuffle_arrival: the responses of an operation arrive in a seeded random
+    order instead of replica order (Client.Read's decision depends on it).  Returns op_off, key_idx, sig,
+    digest, pre_status, ts, value_id and the expected per-item status."""
     rng = np.random.default_rng(seed)
     R, M = n_replicas, n_ops
     by_key = [np.nonzero(pool["key_idx"] == r)[0] for r in range(R)]
     assert all(len(b) for b in by_key), "pool lacks items for some replica key"
     N = M * R
     key_idx = np.tile(np.arange(R, dtype=np.uint32), M)
+    if shuffle_arrival:
+        key_idx = rng.permuted(key_idx.reshape(M, R), axis=1).reshape(N).astype(np.uint32)
     pick = np.empty(N, np.int64)
     for r in range(R):
-        pick[r::R] = by_key[r][rng.integers(0, len(by_key[r]), M)]
-    sig = pool["sig"][pick].copy()
-    digest = pool["digest"][pick].copy()
+        sel = np.nonzero(key_idx == r)[0]
+        pick[sel] = by_key[r][rng.integers(0, len(by_key[r]), len(sel))]
+    sig = pool["sig"][pick]
+    digest = pool["digest"][pick]
     u = rng.random(N)
-    kind = np.where(u < p_ok, 0, np.where(u < p_ok + p_stale, 1, np.where(u < p_ok + p_stale + p_bad, 2, 3)))
+    if mix is None:
+        pk, ps, pb = p_ok, p_stale, p_bad
+    else:
+        cls = rng.choice(len(mix), size=M, p=[m[0] for m in mix])
+        pk = np.repeat(np.array([m[1] for m in mix])[cls], R)
+        ps = np.repeat(np.array([m[2] for m in mix])[cls], R)
+        pb = np.repeat(np.array([m[3] for m in mix])[cls], R)
+    kind = np.where(u < pk, 0, np.where(u < pk + ps, 1, np.where(u < pk + ps + pb, 2, 3)))
     bad = np.nonzero(kind == 2)[0]
     sig[bad, rng.integers(0, 256, len(bad))] ^= np.uint8(0x10)
     pre = np.where(kind == 3, 6, 0).astype(np.uint8)                  # BFTQ_ST_MISSING

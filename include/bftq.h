@@ -77,6 +77,17 @@ typedef struct bftq_engine bftq_engine;
 int  bftq_init(int device, bftq_engine** out);
 void bftq_shutdown(bftq_engine* e);
 const char* bftq_last_error(void);          /* thread-local text of the last failure */
+
+/* Page-locked host memory for the shim's C-side blobs (SURVEY §8b "Ownership": "host shim pins/copies into
+ * page-locked staging").  Go memory cannot be handed to the DMA engine, so the shim's aggregator appends every
+ * request's (tbs, sig) to a blob anyway; when that blob comes from bftq_host_alloc the *_batch calls DMA it in place
+ * instead of copying it through the library's own staging first.  The block is allocated on the NUMA node the
+ * engine's GPU hangs off.  Pageable buffers remain valid inputs everywhere (they are staged). */
+int  bftq_host_alloc(bftq_engine* e, uint64_t bytes, void** out);
+int  bftq_host_free(bftq_engine* e, void* p);
+/* Binds the CALLING thread to the CPUs of the GPU's NUMA node (the library's own worker threads are bound already).
+ * Returns the node number, or -1 when the node is unknown / binding is disabled (BFTQ_NUMA_BIND=0). */
+int  bftq_bind_thread(bftq_engine* e);
 int  bftq_version(void);
 int  bftq_device_sm_count(bftq_engine* e);
 
@@ -201,12 +212,42 @@ int bftq_read_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* 
                           const uint8_t* status, const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops,
                           uint32_t* out_winner, uint8_t* out_bits);
 
+/* Client.Read's decision (protocol/client.go:250-268) exactly as the multicast callback reaches it.  The responders of
+ * an operation are taken IN THE ORDER GIVEN (= arrival order): a response with status 0 is bucketed by (ts, value_id)
+ * (processResponse :207-230) and maxTimestampedValue (:189-205) is asked — only the buckets of the maximum t so far,
+ * IsThreshold over the bucket's responders; any other status joins `failure` and q.Reject(failure) is asked.  The
+ * first decisive response fixes the result, later ones are collected but decide nothing (ch = nil):
+ *   out_decision[i]    BFTQ_READ_VALUE      out_winner[i] = responder index (inside the op) of the first member of
+ *                                           the winning bucket: its value / t are Read's result
+ *                      BFTQ_READ_REJECTED   majorityError(errs, ErrInsufficientNumberOfValidResponses)
+ *                      BFTQ_READ_EXHAUSTED  ErrInsufficientNumberOfResponses (:267)
+ *   out_decided_at[i]  number of responses consumed when the decision fell (1-based; the count for EXHAUSTED)
+ * At most 32 responders per operation. */
+#define BFTQ_READ_VALUE      0
+#define BFTQ_READ_REJECTED   1
+#define BFTQ_READ_EXHAUSTED  2
+int bftq_read_decide_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                           const uint8_t* status, const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops,
+                           uint8_t* out_decision, uint32_t* out_winner, uint32_t* out_decided_at);
+/* K1 + the read decision in one call: every tuple is verified (pre_status as in bftq_verify_tally_batch), then each
+ * operation is decided as bftq_read_decide_batch does.  Host buffers of any size: the operations travel in chunks
+ * through a ring of staging slots, copies overlapping the kernels; bftq_host_alloc memory is DMA'd in place. */
+int bftq_verify_read_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
+                           const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
+                           const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
+                           uint8_t* out_status, uint8_t* out_decision, uint32_t* out_winner, uint32_t* out_decided_at);
+int bftq_verify_read_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint32_t* d_op_off, const uint32_t* d_key_idx,
+                               const uint8_t* d_sig_be, const uint8_t* d_digest, uint32_t hash_alg, const uint8_t* d_pre_status,
+                               const uint64_t* d_ts, const uint32_t* d_value_id, uint64_t n_ops, uint64_t n_items, uint32_t flags,
+                               uint8_t* d_status, uint8_t* d_bits, uint8_t* d_decision, uint32_t* d_winner, uint32_t* d_decided_at,
+                               void* cuda_stream);
+
 /* K1 + K2 in one call (BASELINE configs 3 and 5: "read ops x R-replica quorum, verify + wotqs
  * tally"): verifies all tuples, then tallies per operation on the same stream.  pre_status
  * (nullable) carries per-tuple results decided by the packer (BFTQ_ST_MISSING, _MALFORMED,
  * _HASH_TAG ...): non-zero entries are not verified and keep their status.  ts/value_id nullable:
  * when given, the read tally is produced as in bftq_read_tally_batch, otherwise out_winner is
- * not touched.  Host buffers. */
+ * not touched.  Host buffers of any size (chunked and pipelined like bftq_verify_read_batch). */
 int bftq_verify_tally_batch(bftq_engine* e, const bftq_quorum* q, const uint32_t* op_off, const uint32_t* key_idx,
                             const uint8_t* sig_be, const uint8_t* digest, uint32_t hash_alg, const uint8_t* pre_status,
                             const uint64_t* ts, const uint32_t* value_id, uint64_t n_ops, uint32_t flags,
@@ -228,6 +269,10 @@ int bftq_verify_tally_batch_dev(bftq_engine* e, const bftq_quorum* q, const uint
  * mod m (the reference panics there). */
 int bftq_lagrange_combine_batch(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* x,
                                 const uint8_t* y_be, uint64_t n_items, uint8_t* out_be, uint8_t* out_status);
+/* Same with DEVICE pointers for x / y / out / status (m_be stays a host pointer), enqueued on `cuda_stream` without
+ * synchronising. */
+int bftq_lagrange_combine_batch_dev(bftq_engine* e, const uint8_t* m_be, uint32_t mlen, uint32_t k, const int32_t* d_x,
+                                    const uint8_t* d_y_be, uint64_t n_items, uint8_t* d_out_be, uint8_t* d_status, void* cuda_stream);
 
 /* ---- K5: Lagrange in the exponent -------------------------------------------
  * out[i] = base[i]^exp[i] mod m: big.Int.Exp with a shared odd modulus of exactly 1024 or 2048 bits
@@ -395,6 +440,8 @@ typedef struct {
   uint64_t packer_parse_ns;  /* OpenPGP parsing + keyring lookup + tuple composition                  */
   uint64_t packer_stage_ns;  /* composing the flat inputs in pinned staging + enqueueing copies/kernels */
   uint64_t packer_wait_ns;   /* waiting for a chunk's results                                          */
+  int32_t  numa_node;        /* NUMA node of the engine's GPU (-1 unknown)                             */
+  uint32_t numa_cpus;        /* CPUs the library's worker threads are bound to (0 = not bound)         */
 } bftq_stats_t;
 int bftq_stats(bftq_engine* e, bftq_stats_t* out);
 

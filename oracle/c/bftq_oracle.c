@@ -260,3 +260,54 @@ void orc_tally_batch(const int32_t* params, const uint32_t* moff, const uint64_t
     out[i] = (uint8_t)(is_q | (is_t << 1) | (is_s << 2) | (rej << 3));
   }
 }
+
+/* ------------------------------------------------------------------ read decision ---------- */
+/* Client.Read's multicast callback (protocol/client.go:250-268) over the responders of op i in the order given
+ * (= arrival order): a responder with status != 0 joins `failure` and q.Reject(failure) is tested (wotqs.go:178-185);
+ * one with status == 0 is bucketed by (ts, value_id) (processResponse :207-230) and maxTimestampedValue (:189-205) is
+ * asked: only the buckets of the maximum t so far, the first value (insertion order) whose responders pass IsThreshold
+ * (wotqs.go:157-167, duplicates counted).  The first decisive response fixes the result:
+ *   decision 0 value (winner = index inside the op of the first responder of the winning bucket), 1 rejected,
+ *   2 exhausted (ErrInsufficientNumberOfResponses); decided_at = responses consumed (1-based; count for exhausted). */
+static int in_clique(const uint32_t* moff, const uint64_t* members, uint32_t c, uint64_t id) {
+  for (uint32_t m = moff[c]; m < moff[c + 1]; m++) if (members[m] == id) return 1;
+  return 0;
+}
+void orc_read_decide_batch(const int32_t* params, const uint32_t* moff, const uint64_t* members, uint32_t nqc,
+                           const uint32_t* ooff, const uint64_t* signer_id, const uint8_t* status, const uint64_t* ts,
+                           const uint32_t* value_id, uint64_t n_ops, uint8_t* decision, uint32_t* winner, uint32_t* decided_at) {
+  for (uint64_t i = 0; i < n_ops; i++) {
+    const uint32_t lo = ooff[i], hi = ooff[i + 1];
+    uint8_t dec = 2; uint32_t win = 0xffffffffu, at = hi - lo;
+    for (uint32_t k = lo; k < hi && dec == 2; k++) {
+      if (status[k] == 0) {
+        uint64_t maxt = 0;                                   /* for t, vl := range m { if t >= maxt } */
+        for (uint32_t p = lo; p <= k; p++) if (status[p] == 0 && ts[p] >= maxt) maxt = ts[p];
+        /* values of the max-t bucket set in insertion order */
+        for (uint32_t p = lo; p <= k && dec == 2; p++) {
+          if (status[p] != 0 || ts[p] != maxt) continue;
+          int first = 1;
+          for (uint32_t p2 = lo; p2 < p; p2++) if (status[p2] == 0 && ts[p2] == maxt && value_id[p2] == value_id[p]) { first = 0; break; }
+          if (!first) continue;
+          int is_t = nqc > 0;
+          for (uint32_t c = 0; c < nqc; c++) {
+            int th = params[4 * c + 2], cnt = 0;
+            for (uint32_t p2 = p; p2 <= k; p2++)
+              if (status[p2] == 0 && ts[p2] == maxt && value_id[p2] == value_id[p] && in_clique(moff, members, c, signer_id[p2])) cnt++;
+            if (th > 0 && cnt < th) is_t = 0;
+          }
+          if (is_t) { dec = 0; win = p - lo; at = k - lo + 1; }
+        }
+      } else {
+        int rej = 1;
+        for (uint32_t c = 0; c < nqc; c++) {
+          int f = params[4 * c], fail = 0;
+          for (uint32_t p = lo; p <= k; p++) if (status[p] != 0 && in_clique(moff, members, c, signer_id[p])) fail++;
+          if (f == 0 || fail <= f) rej = 0;
+        }
+        if (rej) { dec = 1; at = k - lo + 1; }
+      }
+    }
+    decision[i] = dec; winner[i] = win; decided_at[i] = at;
+  }
+}

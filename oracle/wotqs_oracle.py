@@ -310,3 +310,30 @@ def max_timestamped_value(m: dict, q: Quorum):
         if q.is_threshold(l):
             return v, maxt
     return None
+
+
+READ_VALUE, READ_REJECTED, READ_EXHAUSTED = 0, 1, 2
+
+
+def read_decide(responses, q: Quorum):
+    """Client.Read's multicast callback, protocol/client.go:250-268, run over `responses` in the order given
+    (= arrival order).  responses: list of (Node, err, t, value) — err truthy when transport.Multicast delivered an
+    error for that peer (signature check of the transport message failed, nonce mismatch, no answer...; then t / value
+    are ignored), else (t, value) are what processResponse (:207-230) parsed out of the answer.
+    Returns (kind, decided_at, value, t): kind READ_VALUE when maxTimestampedValue first returned a value (decided_at =
+    number of responses consumed, 1-based), READ_REJECTED when q.Reject(failure) first held (the reference then reports
+    majorityError(errs, ErrInsufficientNumberOfValidResponses)), READ_EXHAUSTED when the multicast ended without either
+    (ErrInsufficientNumberOfResponses, :267).  Once `ch` has been served the callback keeps collecting but decides
+    nothing more, so the FIRST decisive response fixes the result."""
+    m, failure = {}, []
+    for k, (node, err, t, value) in enumerate(responses):
+        if not err:
+            m.setdefault(t, {}).setdefault(value, []).append(node)            # processResponse: m[t][string(val)]
+            r = max_timestamped_value(m, q)
+            if r is not None:
+                return READ_VALUE, k + 1, r[0], r[1]
+        else:
+            failure.append(node)
+            if q.reject(failure):
+                return READ_REJECTED, k + 1, None, 0
+    return READ_EXHAUSTED, len(responses), None, 0
