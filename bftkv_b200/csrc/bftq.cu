@@ -181,7 +181,11 @@ struct bftq_engine {
   std::vector<bftq::r32::RsaKey32> h_keys32;     // radix-2^32 constants of the same keys
   bftq::r32::RsaKey32* d_keys32 = nullptr;
   std::vector<void*> retired;                    // device key tables replaced by larger ones (freed at shutdown)
+  size_t n_dev_keys = 0;                         // keys fully uploaded and published (what a launch may index)
   bool all_2048 = true;                          // every registered modulus has exactly 2048 bits
+  // Montgomery constants of keys that arrive with a call (VerifyWithCertificate's presented certificate): a bounded
+  // host-side cache, never entered in the device table above (an unauthenticated presenter must not grow engine state)
+  std::map<std::string, std::pair<bftq::RsaKeyDev, bftq::r32::RsaKey32>> cert_consts;
   int rsa_kernel = 0;                            // 0 auto, 28 force radix-2^28, 32 radix-2^32 without / 33 with the dedicated squaring (env BFTQ_RSA_KERNEL)
   std::vector<StagingSlot*> slots;
   bftq_stats_t stats{};
@@ -293,7 +297,14 @@ int acquire_slot(bftq_engine* e, size_t h_bytes, size_t d_bytes, StagingSlot** o
 class Arena {
  public:
   explicit Arena(bftq_engine* e) : e_(e) {}
-  ~Arena() { if (s_) { std::lock_guard<std::mutex> g(e_->mu); s_->busy = false; } }
+  // Work may have been enqueued without finish() having run (an error path returned early): nothing may reuse, regrow
+  // or free the slot's buffers — or the caller's output bounce — under kernels and copies still in flight.
+  ~Arena() {
+    if (!s_) return;
+    if (enqueued_ && s_->stream) cudaStreamSynchronize(s_->stream);
+    std::lock_guard<std::mutex> g(e_->mu);
+    s_->busy = false;
+  }
   // count = elements reserved on the device, copy = elements actually copied (defaults to count)
   template <typename T> void in(T** dptr, const T* host, size_t count, size_t copy = (size_t)-1) {
     add((void**)dptr, (void*)host, count * sizeof(T), (copy == (size_t)-1 ? count : copy) * sizeof(T), true);
@@ -323,6 +334,7 @@ class Arena {
   int upload() {
     int rc = prepare();
     if (rc) return rc;
+    enqueued_ = true;
     uint64_t h2d = 0;
     // Inputs that live in the slot's pinned mirror (staged in place or bounced) have the same layout on
     // both sides, so neighbours travel in ONE copy: a chunk of the packer costs one H2D call, not nine
@@ -382,6 +394,7 @@ class Arena {
     if (!s_) return BFTQ_OK;                          // nothing was enqueued (prepare() failed or was never called)
     if (sleepy_ && recorded_) CU(cudaEventSynchronize(s_->done));
     else CU(cudaStreamSynchronize(s_->stream));
+    enqueued_ = false;
     for (auto* b : bounce_) memcpy(b->host, s_->h_pinned + b->off, b->copy);
     bounce_.clear();
     return BFTQ_OK;
@@ -401,14 +414,27 @@ class Arena {
   }
   bftq_engine* e_;
   StagingSlot* s_ = nullptr;
-  bool sleepy_ = false, recorded_ = false;
+  bool sleepy_ = false, recorded_ = false, enqueued_ = false;
   std::vector<Buf> bufs_;
   std::vector<const Buf*> bounce_;
   size_t total_ = 0;
 };
 
+// The key table a launch indexes: a consistent snapshot of the engine's published table (taken under e->mu), or the
+// table of one call (keys presented with the call).
+struct KeyView {
+  const bftq::RsaKeyDev* d_keys = nullptr;
+  const bftq::r32::RsaKey32* d_keys32 = nullptr;
+  uint32_t nkeys = 0;
+  bool all_2048 = true;
+};
+KeyView global_keys(bftq_engine* e) {
+  std::lock_guard<std::mutex> g(e->mu);
+  return KeyView{e->d_keys, e->d_keys32, (uint32_t)e->n_dev_keys, e->all_2048};
+}
+
 template <int T, int W, int BLOCK, int KB>
-int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
+int launch_rsa(bftq_engine* e, const KeyView& kv, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
                uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st) {
   auto kern = bftq::rsa_verify_kernel<T, W, BLOCK, KB>;
   static thread_local int occ_cache = 0;
@@ -422,23 +448,27 @@ int launch_rsa(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, 
   uint64_t need = (n_items + per_block - 1) / per_block;
   uint64_t grid = std::min<uint64_t>(need, (uint64_t)e->sm_count * occ);
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, BLOCK, 0, st>>>(e->d_keys, (uint32_t)e->h_keys.size(), d_key_idx, d_sig, d_digest, hash_alg,
+  kern<<<(unsigned)grid, BLOCK, 0, st>>>(kv.d_keys, kv.nkeys, d_key_idx, d_sig, d_digest, hash_alg,
                                          n_items, flags, d_pre, d_status);
   CU(cudaGetLastError());
   return BFTQ_OK;
 }
 
-int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
+// exact2048: -1 = decide from the table (every key has exactly 2048 bits), 1 = the caller knows that every key this
+// launch touches has (the packer groups by key), 0 = some do not (radix-2^28 kernel).
+int launch_rsa_any(bftq_engine* e, const KeyView& kv, const uint32_t* d_key_idx, const uint8_t* d_sig, const uint8_t* d_digest,
                    uint32_t hash_alg, uint64_t n_items, uint32_t flags, const uint8_t* d_pre, uint8_t* d_status, cudaStream_t st,
-                   int kb = 256) {
+                   int kb = 256, int exact2048 = -1) {
+  if (!kv.d_keys || !kv.d_keys32) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   {
     std::lock_guard<std::mutex> g(e->mu);
     e->stats.launches += 1;
     e->stats.items += n_items;
   }
-  const bool use32 = kb == 256 && (e->rsa_kernel == 32 || e->rsa_kernel == 33 || (e->rsa_kernel == 0 && e->all_2048));
+  const bool fits32 = exact2048 < 0 ? kv.all_2048 : exact2048 == 1;
+  const bool use32 = kb == 256 && fits32 && e->rsa_kernel != 28;
+  if (kb == 256 && !fits32 && (e->rsa_kernel == 32 || e->rsa_kernel == 33)) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a modulus of the batch is not 2048 bits");
   if (use32) {
-    if (!e->all_2048) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "radix-2^32 kernel forced but a registered modulus is not 2048 bits");
     // rsa_kernel 32 = general products only (mont_mul(y, y)); default / 33 = the squarings go through mont_sqr
     const bool sq = e->rsa_kernel != 32;
     static const int min_blocks = [] { const char* v = getenv("BFTQ_R32_BLOCKS"); return v ? atoi(v) : 4; }();
@@ -451,21 +481,21 @@ int launch_rsa_any(bftq_engine* e, const uint32_t* d_key_idx, const uint8_t* d_s
     const uint64_t per_block = 4 * 8;
     uint64_t grid = std::min<uint64_t>((n_items + per_block - 1) / per_block, (uint64_t)e->sm_count * occ32);
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 128, 0, st>>>(e->d_keys32, (uint32_t)e->h_keys32.size(), d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
+    kern<<<(unsigned)grid, 128, 0, st>>>(kv.d_keys32, kv.nkeys, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
                                          d_pre, d_status);
     CU(cudaGetLastError());
     return BFTQ_OK;
   }
   switch (kb) {
-    case 128: return launch_rsa<4, 10, 128, 128>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
-    case 192: return launch_rsa<4, 14, 128, 192>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
-    case 384: return launch_rsa<8, 14, 128, 384>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
-    case 512: return launch_rsa<8, 19, 128, 512>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 128: return launch_rsa<4, 10, 128, 128>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 192: return launch_rsa<4, 14, 128, 192>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 384: return launch_rsa<8, 14, 128, 384>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+    case 512: return launch_rsa<8, 19, 128, 512>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
     case 256: break;
     default: return fail(BFTQ_ERR_UNSUPPORTED_KEY, "key size class not built (128/192/256/384/512 bytes are)");
   }
-  if (e->rsa_t == 8) return launch_rsa<8, 10, 128, 256>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
-  return launch_rsa<4, 19, 128, 256>(e, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+  if (e->rsa_t == 8) return launch_rsa<8, 10, 128, 256>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
+  return launch_rsa<4, 19, 128, 256>(e, kv, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags, d_pre, d_status, st);
 }
 
 // ---- integer-pipe peak micro-benchmark ---------------------------------------------------------
@@ -583,13 +613,63 @@ int bftq_device_sm_count(bftq_engine* e) { return e ? e->sm_count : BFTQ_ERR_INV
 int bftq_key_count(bftq_engine* e) {
   if (!e) return BFTQ_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(e->mu);
-  return (int)e->h_keys.size();
+  return (int)e->n_dev_keys;
 }
 
 int bftq_register_rsa_keys(bftq_engine* e, const uint8_t* n_be, const uint32_t* exps, uint32_t count,
                            uint32_t* first_index) {
   return bftq_register_rsa_keys_k(e, n_be, 256, exps, count, first_index);
 }
+
+}  // extern "C"
+namespace {
+// Per-key Montgomery constants for both kernel families from a big-endian modulus.  *is2048: exactly 2048 bits.
+int make_key_consts(const uint8_t* n_be, uint32_t stride, uint32_t exp, bftq::RsaKeyDev& kd, bftq::r32::RsaKey32& k32, bool* is2048) {
+  UBig n;
+  from_be(n, n_be, stride);
+  const int nb = bitlen(n);
+  const int kb = (nb + 7) / 8;
+  const int cls = bftq::class_of(kb);
+  if (!cls || !(n.w[0] & 1)) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd and at most 4096 bits");
+  if (exp == 0) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "public exponent 0");
+  memset(&kd, 0, sizeof(kd));
+  to_digits(n, kd.n, bftq::kMaxDigits);
+  // -n^-1 mod 2^32 by Newton iteration on the low word (masked to 28 bits for the digit kernels).
+  uint32_t n0 = (uint32_t)n.w[0], inv = n0;
+  for (int i = 0; i < 5; i++) inv *= 2u - n0 * inv;
+  kd.n0inv = (0u - inv) & bftq::kDigitMask;
+  kd.e = exp;
+  kd.nbits = (uint32_t)nb;
+  kd.kbytes = (uint32_t)kb;
+  // R^2 mod n for each digit layout of the class: 2^(2*28*digits) by repeated doubling from 1.
+  UBig x;
+  memset(&x, 0, sizeof(x));
+  x.w[0] = 1;
+  int exp2 = 0;
+  for (int layout = 0; layout < bftq::kNumLayouts; layout++) {
+    const int digits = bftq::class_digits(cls, layout == 1 && cls != 256 ? 0 : layout);
+    const int target = 2 * 28 * digits;
+    while (exp2 < target) { dbl_mod(x, n); exp2++; }
+    if (exp2 == target) to_digits(x, kd.r2[layout], bftq::kMaxDigits);
+  }
+  // radix-2^32 constants (fast path, meaningful for exactly-2048-bit moduli): n, 2^4096 mod n, -n^-1 mod 2^32
+  memset(&k32, 0, sizeof(k32));
+  for (int i = 0; i < 32; i++) { k32.n[2 * i] = (uint32_t)n.w[i]; k32.n[2 * i + 1] = (uint32_t)(n.w[i] >> 32); }
+  k32.n0inv = 0u - inv;
+  k32.e = exp;
+  k32.nbits = (uint32_t)nb;
+  if (nb == 2048) {
+    UBig y;
+    memset(&y, 0, sizeof(y));
+    y.w[0] = 1;
+    for (int ex = 0; ex < 4096; ex++) dbl_mod(y, n);
+    for (int i = 0; i < 32; i++) { k32.r2[2 * i] = (uint32_t)y.w[i]; k32.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
+  }
+  if (is2048) *is2048 = !(cls == 256 && nb != 2048);
+  return BFTQ_OK;
+}
+}  // namespace
+extern "C" {
 
 int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t stride, const uint32_t* exps, uint32_t count,
                              uint32_t* first_index) {
@@ -599,77 +679,47 @@ int bftq_register_rsa_keys_k(bftq_engine* e, const uint8_t* n_be, uint32_t strid
   std::vector<bftq::r32::RsaKey32> fresh32(count);
   bool fresh_all_2048 = true;
   for (uint32_t k = 0; k < count; k++) {
-    UBig n;
-    from_be(n, n_be + (size_t)k * stride, stride);
-    const int nb = bitlen(n);
-    const int kb = (nb + 7) / 8;
-    const int cls = bftq::class_of(kb);
-    if (!cls || !(n.w[0] & 1))
-      return fail(BFTQ_ERR_UNSUPPORTED_KEY, "modulus must be odd and at most 4096 bits (key " + std::to_string(k) + ")");
-    if (exps[k] == 0) return fail(BFTQ_ERR_UNSUPPORTED_KEY, "public exponent 0");
-    bftq::RsaKeyDev& kd = fresh[k];
-    memset(&kd, 0, sizeof(kd));
-    to_digits(n, kd.n, bftq::kMaxDigits);
-    // -n^-1 mod 2^32 by Newton iteration on the low word (masked to 28 bits for the digit kernels).
-    uint32_t n0 = (uint32_t)n.w[0], inv = n0;
-    for (int i = 0; i < 5; i++) inv *= 2u - n0 * inv;
-    kd.n0inv = (0u - inv) & bftq::kDigitMask;
-    kd.e = exps[k];
-    kd.nbits = (uint32_t)nb;
-    kd.kbytes = (uint32_t)kb;
-    // R^2 mod n for each digit layout of the class: 2^(2*28*digits) by repeated doubling from 1.
-    UBig x;
-    memset(&x, 0, sizeof(x));
-    x.w[0] = 1;
-    int exp2 = 0;
-    for (int layout = 0; layout < bftq::kNumLayouts; layout++) {
-      const int digits = bftq::class_digits(cls, layout == 1 && cls != 256 ? 0 : layout);
-      const int target = 2 * 28 * digits;
-      while (exp2 < target) { dbl_mod(x, n); exp2++; }
-      if (exp2 == target) to_digits(x, kd.r2[layout], bftq::kMaxDigits);
-    }
-    // radix-2^32 constants (fast path, meaningful for exactly-2048-bit moduli): n, 2^4096 mod n, -n^-1 mod 2^32
-    bftq::r32::RsaKey32& k32 = fresh32[k];
-    memset(&k32, 0, sizeof(k32));
-    for (int i = 0; i < 32; i++) { k32.n[2 * i] = (uint32_t)n.w[i]; k32.n[2 * i + 1] = (uint32_t)(n.w[i] >> 32); }
-    k32.n0inv = 0u - inv;
-    k32.e = exps[k];
-    k32.nbits = (uint32_t)nb;
-    if (nb == 2048) {
-      UBig y;
-      memset(&y, 0, sizeof(y));
-      y.w[0] = 1;
-      for (int ex = 0; ex < 4096; ex++) dbl_mod(y, n);
-      for (int i = 0; i < 32; i++) { k32.r2[2 * i] = (uint32_t)y.w[i]; k32.r2[2 * i + 1] = (uint32_t)(y.w[i] >> 32); }
-    }
-    if (cls == 256 && nb != 2048) fresh_all_2048 = false;
+    bool is2048 = true;
+    const int rc = make_key_consts(n_be + (size_t)k * stride, stride, exps[k], fresh[k], fresh32[k], &is2048);
+    if (rc) return fail(rc, g_last_error + " (key " + std::to_string(k) + ")");
+    fresh_all_2048 = fresh_all_2048 && is2048;
   }
+  // Publication order (launchers snapshot {pointers, count, all_2048} under the same mutex, global_keys()): the new
+  // keys are on the device — synchronously — BEFORE the count that makes them reachable moves, a larger table is
+  // complete before its pointer replaces the old one, and host state changes only after every CUDA call succeeded.
   std::lock_guard<std::mutex> g(e->mu);
   CU(cudaSetDevice(e->device));
-  const size_t old = e->h_keys.size();
-  e->h_keys.insert(e->h_keys.end(), fresh.begin(), fresh.end());
-  e->h_keys32.insert(e->h_keys32.end(), fresh32.begin(), fresh32.end());
-  e->all_2048 = e->all_2048 && fresh_all_2048;
-  if (e->h_keys.size() > e->d_keys_cap) {
-    // Kernels in flight — or being launched right now by other callers, with the old pointer already read — may
-    // still use the old table: it is retired, not freed (2.4 KB per key; released at bftq_shutdown), so growing the
-    // keyring while batches are being verified is safe.
-    size_t cap = std::max<size_t>(64, e->h_keys.size() * 2);
+  const size_t old = e->n_dev_keys, want = old + count;
+  if (want > e->d_keys_cap) {
+    // Kernels in flight may still read the old table: it is retired, not freed (released at bftq_shutdown).  The
+    // table grows only with the keyring (keys that arrive with a call never enter it), so this is bounded.
+    const size_t cap = std::max<size_t>(64, want * 2);
     bftq::RsaKeyDev* nd = nullptr;
     bftq::r32::RsaKey32* nd32 = nullptr;
-    CU(cudaMalloc((void**)&nd, cap * sizeof(bftq::RsaKeyDev)));
-    CU(cudaMalloc((void**)&nd32, cap * sizeof(bftq::r32::RsaKey32)));
+    if (cudaMalloc((void**)&nd, cap * sizeof(bftq::RsaKeyDev)) != cudaSuccess) return fail(BFTQ_ERR_NOMEM, "key table allocation failed");
+    if (cudaMalloc((void**)&nd32, cap * sizeof(bftq::r32::RsaKey32)) != cudaSuccess) { cudaFree(nd); return fail(BFTQ_ERR_NOMEM, "key table allocation failed"); }
+    cudaError_t ce = cudaSuccess;
+    if (old) {
+      ce = cudaMemcpy(nd, e->h_keys.data(), old * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice);
+      if (ce == cudaSuccess) ce = cudaMemcpy(nd32, e->h_keys32.data(), old * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice);
+    }
+    if (ce == cudaSuccess && count) ce = cudaMemcpy(nd + old, fresh.data(), count * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && count) ce = cudaMemcpy(nd32 + old, fresh32.data(), count * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(nd); cudaFree(nd32); return fail(BFTQ_ERR_CUDA, std::string("key table upload: ") + cudaGetErrorString(ce)); }
     if (e->d_keys) e->retired.push_back(e->d_keys);
     if (e->d_keys32) e->retired.push_back(e->d_keys32);
     e->d_keys = nd;
     e->d_keys32 = nd32;
     e->d_keys_cap = cap;
-    CU(cudaMemcpy(e->d_keys, e->h_keys.data(), e->h_keys.size() * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(e->d_keys32, e->h_keys32.data(), e->h_keys32.size() * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice));
-  } else {
-    CU(cudaMemcpy(e->d_keys + old, e->h_keys.data() + old, count * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(e->d_keys32 + old, e->h_keys32.data() + old, count * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice));
+  } else if (count) {
+    // slots [old, want) are beyond every published count: no launch reads them yet
+    CU(cudaMemcpy(e->d_keys + old, fresh.data(), count * sizeof(bftq::RsaKeyDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_keys32 + old, fresh32.data(), count * sizeof(bftq::r32::RsaKey32), cudaMemcpyHostToDevice));
   }
+  e->h_keys.insert(e->h_keys.end(), fresh.begin(), fresh.end());
+  e->h_keys32.insert(e->h_keys32.end(), fresh32.begin(), fresh32.end());
+  e->all_2048 = e->all_2048 && fresh_all_2048;
+  e->n_dev_keys = want;
   if (first_index) *first_index = (uint32_t)old;
   return BFTQ_OK;
 }
@@ -687,9 +737,8 @@ int bftq_rsa_verify_batch_dev_k(bftq_engine* e, uint32_t key_bytes, const uint32
   if (!e || !d_key_idx || !d_sig_be || !d_digest || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (bftq::host_hash_dlen(hash_alg) == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_items == 0) return BFTQ_OK;
-  if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   CU(cudaSetDevice(e->device));
-  return launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, nullptr, d_status, (cudaStream_t)cuda_stream, (int)key_bytes);
+  return launch_rsa_any(e, global_keys(e), d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, nullptr, d_status, (cudaStream_t)cuda_stream, (int)key_bytes);
 }
 
 int bftq_rsa_verify_batch(bftq_engine* e, const uint32_t* key_idx, const uint8_t* sig_be, const uint8_t* digest,
@@ -704,7 +753,8 @@ int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* 
   const int dlen = bftq::host_hash_dlen(hash_alg);
   if (dlen == 0) return fail(BFTQ_ERR_INVALID_ARG, "unknown hash algorithm id");
   if (n_items == 0) return BFTQ_OK;
-  if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
+  const KeyView kv = global_keys(e);
+  if (!kv.d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
   // Large batches are cut into chunks that travel through a ring of staging slots (one stream each): the copy of
   // chunk c+1 runs under the kernel of chunk c, and kernels of neighbouring chunks run out of phase
   // (tools/e2e_experiment.py: 33.8 M/s for one caller unchunked, ~50 M/s with four 16384-item pieces in flight).
@@ -727,7 +777,7 @@ int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* 
     a.out(&d_st, out_status + lo, (size_t)cnt);
     rc = a.upload();
     if (rc) break;
-    rc = launch_rsa_any(e, d_idx, d_sig, d_dig, hash_alg, cnt, flags, nullptr, d_st, a.stream(), (int)key_bytes);
+    rc = launch_rsa_any(e, kv, d_idx, d_sig, d_dig, hash_alg, cnt, flags, nullptr, d_st, a.stream(), (int)key_bytes);
     if (rc) break;
     rc = a.download_async();
   }
@@ -947,8 +997,7 @@ static int verify_tally_dev_impl(bftq_engine* e, const bftq_quorum* q, const uin
   if (n_ops == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
   if (n_items) {
-    if (!e->d_keys) return fail(BFTQ_ERR_INVALID_ARG, "no keys registered");
-    int rc = launch_rsa_any(e, d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_pre_status, d_status, st);
+    int rc = launch_rsa_any(e, global_keys(e), d_key_idx, d_sig_be, d_digest, hash_alg, n_items, flags, d_pre_status, d_status, st);
     if (rc) return rc;
   }
   return launch_tally(e, q, d_op_off, d_key_idx, d_status, d_ts, d_value_id, n_ops, d_winner, d_bits, st, d_decision, d_decided_at);

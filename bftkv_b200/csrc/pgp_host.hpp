@@ -38,14 +38,18 @@ struct Reader {
 };
 
 // One packet.  `body` points into the input unless the packet used partial lengths, in which case
-// it points into `scratch`.  Framing errors exhaust the reader (x/crypto hits io.ErrUnexpectedEOF).
+// it points into `scratch`.  A truncated length or body exhausts the reader (x/crypto's readFull runs into
+// io.ErrUnexpectedEOF with everything consumed); a tag byte without the MSB consumes exactly that ONE byte
+// (packet.readHeader reads one byte and returns StructuralError), so CollectiveSignature.Verify's loop
+// `for r.Len() > 0` (crypto_pgp.go:489) resynchronises on the next byte: a stray byte from one Byzantine
+// responder must not hide the honest signatures behind it.
 inline int read_packet(Reader& r, int& tag, const uint8_t*& body, size_t& blen, std::vector<uint8_t>& scratch) {
   if (r.pos >= r.len) return kEof;
   const uint8_t* d = r.d;
   const size_t n = r.len;
   const uint8_t hdr = d[r.pos];
   auto bad = [&]() { r.pos = n; return (int)kStructural; };
-  if (!(hdr & 0x80)) return bad();
+  if (!(hdr & 0x80)) { r.pos += 1; return (int)kStructural; }
   size_t p = r.pos + 1;
   if (!(hdr & 0x40)) {                       // old format
     tag = (hdr & 0x3f) >> 2;

@@ -76,14 +76,16 @@ class Reader:
 
 
 def read_packet(r: Reader) -> Optional[Tuple[int, bytes]]:
-    """Returns (tag, body) or None at a clean EOF.  Raises StructuralError on bad framing
-    (the reader is then exhausted: x/crypto would have hit io.ErrUnexpectedEOF)."""
+    """Returns (tag, body) or None at a clean EOF.  Raises StructuralError on bad framing: a truncated
+    length or body exhausts the reader (x/crypto's readFull hits io.ErrUnexpectedEOF with everything
+    consumed); a tag byte without the MSB consumes exactly that one byte (packet.readHeader reads ONE byte
+    before returning StructuralError), so a caller that ignores errors resynchronises on the next byte."""
     d = r.data
     if r.pos >= len(d):
         return None
     hdr = d[r.pos]
     if hdr & 0x80 == 0:
-        r.pos = len(d)
+        r.pos += 1
         raise StructuralError("tag byte does not have MSB set")
     try:
         if hdr & 0x40 == 0:                       # old format

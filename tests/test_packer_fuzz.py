@@ -168,3 +168,21 @@ def test_gpu_fast_parser_agrees_with_host_parser(golden):
     tried, fast, bad = (int(x) for x in r.stdout.split())
     assert r.returncode == 0 and bad == 0, r.stderr[-2000:]
     assert tried > 1500000 and fast > 100000                     # the fast path is actually exercised
+
+
+def test_collective_walk_resynchronises_after_stray_bytes(env, golden):
+    """CollectiveSignature.Verify ignores errors (crypto_pgp.go:489-497) and x/crypto's readHeader consumes ONE byte when
+    the tag byte has no MSB, so stray low bytes a Byzantine responder slipped between two packets cost nothing: every
+    honest signature around them is still reached.  Signature.Verify's strict walk fails at the first stray byte."""
+    kr, sig, ents = env
+    sigs = [bytes.fromhex(c["sig"]) for c in golden["cases"]]
+    known = [s for s in sigs if oracle_walk(ents, s, False) == ([oracle_walk(ents, s, False)[0][0]] if oracle_walk(ents, s, False)[0] else [], False)
+             and len(oracle_walk(ents, s, False)[0]) == 1][:3]
+    assert len(known) == 3
+    issuers = [oracle_walk(ents, s, False)[0][0] for s in known]
+    for junk in (b"\x00", b"\x7f", b"\x01\x02\x03", b"\x00" * 17):
+        data = known[0] + junk + known[1] + junk + known[2]
+        assert oracle_walk(ents, data, True) == (issuers, False)
+        assert sig.parse(data, True) == (issuers, False)
+        assert sig.parse(data, False) == ([issuers[0]], True) == oracle_walk(ents, data, False)
+        assert sig.parse(junk + known[0], True) == ([issuers[0]], False) == oracle_walk(ents, junk + known[0], True)
