@@ -183,8 +183,11 @@ def run_gpu(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: whatever libraries write to fd 1 meanwhile (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cores_rank = max(1, host_cores() // world)
@@ -277,10 +280,22 @@ def run_gpu(args, rank, local_rank, world):
             eng.rsa_verify_batch(h_in[c][0], h_in[c][1], h_in[c][2], out=h_in[c][3])
 
     def run_callers(fn, shares):
-        ths = [threading.Thread(target=fn, args=(c, shares[c])) for c in range(len(shares))]
+        """Runs fn(c, shares[c]) on one thread per caller; returns the seconds from the common start signal (given once
+        every thread exists and waits — thread creation is not part of a step) to the last caller's return + device sync."""
+        gun = threading.Event()
+
+        def body(c):
+            eng.bind_thread()
+            gun.wait()
+            fn(c, shares[c])
+        ths = [threading.Thread(target=body, args=(c,)) for c in range(len(shares))]
         [t.start() for t in ths]
+        time.sleep(0.002)
+        t_start = time.perf_counter()
+        gun.set()
         [t.join() for t in ths]
         torch.cuda.synchronize(dev)
+        return time.perf_counter() - t_start
 
     def split(n, k):
         return [n // k + (1 if c < n % k else 0) for c in range(k)]
@@ -289,9 +304,7 @@ def run_gpu(args, rank, local_rank, world):
     # slots on demand, and callers running together need more of them than one caller alone
     run_callers(caller, [args.warmup] * NCALLERS)
     barrier()
-    t0 = time.perf_counter()
-    run_callers(caller, share)
-    e2e_s = time.perf_counter() - t0
+    e2e_s = run_callers(caller, share)
     barrier()
     for c in range(NCALLERS):
         if share[c]:
@@ -341,9 +354,7 @@ def run_gpu(args, rank, local_rank, world):
     pshare = split(args.steps, PCALLERS)
     st0, thr0 = eng.stats(), cgroup_throttled()
     barrier()
-    t0 = time.perf_counter()
-    run_callers(pgp_pinned, pshare)
-    pgp_s = time.perf_counter() - t0
+    pgp_s = run_callers(pgp_pinned, pshare)
     barrier()
     st1, thr1 = eng.stats(), cgroup_throttled()
     for c in range(PCALLERS):
@@ -353,9 +364,7 @@ def run_gpu(args, rank, local_rank, world):
     n_e2e_sus = max(args.steps, int(args.sustain / max(pgp_s / args.steps, 1e-6)) + 1)
     barrier()
     m2 = sampler.mark()
-    t0 = time.perf_counter()
-    run_callers(pgp_pinned, split(n_e2e_sus, PCALLERS))
-    pgp_sus_s = time.perf_counter() - t0
+    pgp_sus_s = run_callers(pgp_pinned, split(n_e2e_sus, PCALLERS))
     m3 = sampler.mark()
     barrier()
     t0 = time.perf_counter()
@@ -365,17 +374,13 @@ def run_gpu(args, rank, local_rank, world):
     run_callers(pgp_pageable, [args.warmup] * PCALLERS)
     sp0 = eng.stats()
     barrier()
-    t0 = time.perf_counter()
-    run_callers(pgp_pageable, pshare)
-    pgp_pageable_s = time.perf_counter() - t0
+    pgp_pageable_s = run_callers(pgp_pageable, pshare)
     barrier()
     sp1 = eng.stats()
     # the same leg with the packets parsed by the host packer (BFTQ_GPU_PARSE=0) instead of K0, for context
     os.environ["BFTQ_GPU_PARSE"] = "0"
     run_callers(pgp_pinned, [args.warmup] * PCALLERS)
-    t0 = time.perf_counter()
-    run_callers(pgp_pinned, pshare)
-    host_packer_s = time.perf_counter() - t0
+    host_packer_s = run_callers(pgp_pinned, pshare)
     del os.environ["BFTQ_GPU_PARSE"]
     for c in range(PCALLERS):
         if pshare[c]:
@@ -687,7 +692,8 @@ def run_gpu(args, rank, local_rank, world):
                                % (reps, reps * ITEMS, threads, CPU_KIND_TEXT[kind])}
         out["cpu_baseline_port"] = {"value": port_rate, "unit": "verifies/s", "cores": threads, "kind": "port", "implementation": "port",
                                     "sample": "%d passes over the same batch; %s" % (reps, CPU_KIND_TEXT["port"])}
-    print(json.dumps(out))
+    real_stdout.write(json.dumps(out) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
