@@ -20,7 +20,12 @@ from .engine import Engine, QC, TALLY_IS_QUORUM, TALLY_IS_SUFFICIENT, TALLY_IS_T
 
 ErrInvalidSignature = "crypto: invalid signature"
 ErrInsufficientNumberOfSignatures = "crypto: insufficient number of signatures"
-_ERR = {0: None, -6: ErrInvalidSignature, -7: ErrInsufficientNumberOfSignatures}
+ErrDecryptionFailed = "crypto: decryption failed"
+ErrInvalidTransportSecurityData = "crypto: invalid transport security data"
+ErrMessageBody = "message body / nonce error"
+ErrMessageUnsupported = "unsupported message form (compressed data)"
+_ERR = {0: None, -6: ErrInvalidSignature, -7: ErrInsufficientNumberOfSignatures, -8: ErrDecryptionFailed, -9: ErrInvalidTransportSecurityData,
+        -10: ErrMessageBody, -11: ErrMessageUnsupported}
 
 
 def _blob(items: Sequence[bytes]):
@@ -280,3 +285,37 @@ class QuorumSystem:
         if self._h:
             self._lib.bftq_graph_destroy(self._h)
             self._h = None
+
+
+class Message:
+    """crypto.Message's Decrypt (crypto/crypto.go:60-64, crypto_pgp.go:453-471), signature half: the host has already
+    removed the encryption layer; each item is the packet stream inside (one-pass signature, literal data, signature)."""
+
+    def __init__(self, keyring: "Keyring"):
+        self.kr = keyring
+
+    def decrypt_verify_batch(self, streams: Sequence[bytes]):
+        """-> list of dict(err, plain, nonce, signed_by_key_id, signer_known, binary)."""
+        n = len(streams)
+        if n == 0:
+            return []
+        blob, off = _blob(streams)
+        total = int(off[-1])
+        err = np.zeros(n, np.int32)
+        by = np.zeros(n, np.uint64)
+        flags = np.zeros(n, np.uint8)
+        plain, nonce = np.zeros(max(total, 1), np.uint8), np.zeros(max(total, 1), np.uint8)
+        plen, nlen = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(self.kr._lib.bftq_message_verify_batch(self.kr._h, p(blob), p(off), n, p(err), p(by), p(flags), p(plain), p(plen), p(nonce), p(nlen)))
+        out = []
+        for i in range(n):
+            o = int(off[i])
+            ok_body = int(err[i]) in (0, -6)
+            out.append({"err": _ERR[int(err[i])], "plain": bytes(plain[o:o + int(plen[i])]) if ok_body else None,
+                        "nonce": bytes(nonce[o:o + int(nlen[i])]) if ok_body else None, "signed_by_key_id": int(by[i]),
+                        "signer_known": bool(flags[i] & 1), "binary": bool(flags[i] & 2)})
+        return out
+
+    def decrypt_verify(self, stream: bytes):
+        return self.decrypt_verify_batch([stream])[0]

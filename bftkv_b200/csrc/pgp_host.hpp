@@ -87,6 +87,14 @@ inline int read_packet(Reader& r, int& tag, const uint8_t*& body, size_t& blen, 
   }
 }
 
+// Tag of the packet the reader stands at == literal data (11)?  (peek only)
+inline bool tag_is_literal(const Reader& r) {
+  if (r.pos >= r.len) return false;
+  const uint8_t hdr = r.d[r.pos];
+  if (!(hdr & 0x80)) return false;
+  return ((hdr & 0x40) ? (hdr & 0x3f) : ((hdr & 0x3f) >> 2)) == 11;
+}
+
 struct Span {
   const uint8_t* p = nullptr; size_t n = 0;
   const uint8_t* data() const { return p; }
@@ -391,6 +399,105 @@ inline int next_known_signature(Reader& r, const std::vector<const std::vector<E
     keys_by_id_usage(rings, sig.issuer, kKeyFlagSign, keys);
     if (!keys.empty()) return kOk;
   }
+}
+
+}}  // namespace bftq::pgp
+
+// ---- transport messages: PGPMessage.Decrypt's signature half (crypto_pgp.go:453-471) -------------------------------
+// openpgp.ReadMessage's readSignedMessage walk over the packet stream a SymmetricallyEncrypted packet decrypts to:
+// [compressed] one-pass signature (tag 4), literal data (tag 11), signature (tag 2).  Restated from the published
+// golang.org/x/crypto/openpgp/read.go @53104e6ec876 (not in the reference tree); oracle/pgp_oracle.py message_verify
+// is the same walk in Python.
+namespace bftq { namespace pgp {
+
+enum : int { kMsgOk = 0, kMsgReadFailed = 1 /* ReadMessage error -> ErrDecryptionFailed */, kMsgNotSigned = 2 /* ErrInvalidTransportSecurityData */,
+              kMsgCompressed = 3 /* compressed data packet: not handled here */, kMsgBodyFailed = 4 /* the literal body ends early: ReadAll's error */ };
+
+struct MessageHead {
+  bool has_ops = false;
+  uint8_t ops_sig_type = 0, ops_hash = 0, ops_pk_algo = 0;
+  uint64_t ops_key_id = 0;
+  bool binary = false;
+  const uint8_t* name = nullptr; size_t name_len = 0;       // literal FileName (views into the packet body)
+  const uint8_t* body = nullptr; size_t body_len = 0;       // literal data, de-chunked
+};
+
+// Walks to the literal data packet.  On kMsgOk the reader stands behind the literal packet; `scratch` owns the body when
+// the packet used partial lengths (what Go's own writer always emits), so it must outlive `h`.
+inline int read_message_head(Reader& r, MessageHead& h, std::vector<uint8_t>& scratch) {
+  h = MessageHead();
+  std::vector<uint8_t> tmp;
+  for (;;) {
+    int tag; const uint8_t* body; size_t bl;
+    const bool at_literal = tag_is_literal(r);
+    const int rc = read_packet(r, tag, body, bl, at_literal ? scratch : tmp);
+    // a literal packet that ends early is discovered by ioutil.ReadAll(UnverifiedBody), after the IsSigned check
+    if (rc) return rc != kEof && at_literal ? (h.has_ops ? kMsgBodyFailed : kMsgNotSigned) : kMsgReadFailed;   // EOF: packets.Next() -> io.EOF -> ReadMessage fails
+    if (!known_tag(tag)) continue;
+    if (tag == 8) return kMsgCompressed;                     // compressed data: not handled (bftkv's own Encrypt never compresses)
+    if (tag == 4) {
+      if (bl < 13) return kMsgReadFailed;
+      if (body[0] != 3) return kMsgReadFailed;               // UnsupportedError("one-pass-signature packet version")
+      if (!hash_digest_len(body[2])) return kMsgReadFailed;  // UnsupportedError("hash function")
+      if (!body[12]) return kMsgReadFailed;                  // UnsupportedError("nested signatures")
+      if (body[2] == 3) return kMsgReadFailed;               // hashForSignature: crypto.RIPEMD160 is not linked into bftkv
+      if (body[1] != 0x00 && body[1] != 0x01) return kMsgReadFailed;   // hashForSignature: unsupported signature type
+      h.has_ops = true; h.ops_sig_type = body[1]; h.ops_hash = body[2]; h.ops_pk_algo = body[3];
+      h.ops_key_id = 0; for (int i = 0; i < 8; i++) h.ops_key_id = (h.ops_key_id << 8) | body[4 + i];
+    } else if (tag == 2) {
+      SigPacket s;
+      if (parse_signature(body, bl, s)) return kMsgReadFailed;          // parsed by packet.Read, ignored by the switch
+    } else if (tag == 11) {
+      if (bl < 2 || bl < (size_t)2 + body[1] + 4) return kMsgReadFailed;
+      h.binary = body[0] == 'b';
+      h.name = body + 2; h.name_len = body[1];
+      h.body = body + 6 + body[1]; h.body_len = bl - 6 - body[1];
+      return h.has_ops ? kMsgOk : kMsgNotSigned;
+    }
+  }
+}
+
+// encoding/base64 StdEncoding.DecodeString (Go 1.13): CR / LF skipped anywhere, padding mandatory, nothing but CR / LF
+// after it, trailing bits unchecked.  Returns false on CorruptInputError.  out may hold up to 3 * n / 4 bytes.
+inline bool go_base64_std_decode(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+  out.clear();
+  auto val = [](uint8_t c) -> int {
+    if (c >= 'A' && c <= 'Z') return c - 'A';
+    if (c >= 'a' && c <= 'z') return c - 'a' + 26;
+    if (c >= '0' && c <= '9') return c - '0' + 52;
+    if (c == '+') return 62;
+    if (c == '/') return 63;
+    return -1;
+  };
+  uint8_t q[4] = {0, 0, 0, 0}; int nq = 0; bool closed = false;
+  size_t i = 0;
+  auto flush = [&](int have) { // have = data characters of the quantum (2..4)
+    const int v0 = val(q[0]), v1 = val(q[1]), v2 = have > 2 ? val(q[2]) : 0, v3 = have > 3 ? val(q[3]) : 0;
+    out.push_back((uint8_t)((v0 << 2) | (v1 >> 4)));
+    if (have > 2) out.push_back((uint8_t)(((v1 & 15) << 4) | (v2 >> 2)));
+    if (have > 3) out.push_back((uint8_t)(((v2 & 3) << 6) | v3));
+  };
+  for (; i < n; i++) {
+    const uint8_t c = src[i];
+    if (c == '\r' || c == '\n') continue;
+    if (closed) return false;                                  // data after the padding
+    if (c == '=') {
+      if (nq < 2) return false;
+      if (nq == 2) {                                           // 'xx==' : the next significant byte must be '='
+        size_t j = i + 1;
+        while (j < n && (src[j] == '\r' || src[j] == '\n')) j++;
+        if (j >= n || src[j] != '=') return false;
+        i = j;
+      }
+      flush(nq);
+      nq = 0; closed = true;
+      continue;
+    }
+    if (val(c) < 0) return false;
+    q[nq++] = c;
+    if (nq == 4) { flush(4); nq = 0; }
+  }
+  return nq == 0;
 }
 
 }}  // namespace bftq::pgp

@@ -270,3 +270,59 @@ def sig_packet_v4(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_typ
     d = hashlib.new(_HASHLIB[hash_id], signed + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
     unhashed = bytes([9, 16]) + struct.pack(">Q", key_id)
     return _old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + d[:2] + _mpi(raw_rsa_sign(k, hash_id, d)))
+
+
+# ---- transport messages: what openpgp.Encrypt(signer) puts inside the SymmetricallyEncrypted packet --------------------
+# crypto_pgp.go:418-451 (Message.Encrypt / EncryptStream): one-pass signature, literal data (binary, FileName =
+# base64(nonce), time 0), signature — each written by x/crypto's serializers: new-format headers, and the literal data
+# through packet.serializeStreamHeader's partialLengthWriter, which turns EVERY Write into power-of-two partial chunks.
+
+def _new_packet(tag: int, body: bytes) -> bytes:
+    n = len(body)
+    if n < 192:
+        ln = bytes([n])
+    elif n < 8384:
+        ln = bytes([((n - 192) >> 8) + 192, (n - 192) & 0xFF])
+    else:
+        ln = b"\xff" + struct.pack(">I", n)
+    return bytes([0xC0 | tag]) + ln + body
+
+
+def go_partial_write(data: bytes) -> bytes:
+    """packet.partialLengthWriter.Write (x/crypto @53104e6ec876): the largest power of two that fits, repeatedly."""
+    out, p = bytearray(), 0
+    while p < len(data):
+        for power in range(14, -1, -1):
+            l = 1 << power
+            if len(data) - p >= l:
+                out.append(224 + power)
+                out += data[p:p + l]
+                p += l
+                break
+    return bytes(out)
+
+
+def go_literal_packet(plain: bytes, file_name: bytes, binary: bool = True, time: int = 0) -> bytes:
+    """packet.SerializeLiteral + Write(plain) + Close: four Writes (format+len, name, time, body), then a zero length."""
+    body = go_partial_write(bytes([ord("b") if binary else ord("t"), len(file_name)])) + go_partial_write(file_name) + \
+        go_partial_write(struct.pack(">I", time)) + go_partial_write(plain)
+    return bytes([0xC0 | 11]) + body + b"\x00"
+
+
+def one_pass_packet(sig_type: int, hash_id: int, pk_algo: int, key_id: int, is_last: int = 1) -> bytes:
+    return _new_packet(4, bytes([3, sig_type, hash_id, pk_algo]) + struct.pack(">Q", key_id) + bytes([is_last]))
+
+
+def go_signature_packet(k, key_id: int, hash_id: int, signed: bytes, ctime: int, sig_type: int = 0) -> bytes:
+    """packet.Signature.Serialize after Sign: v4, hashed area = creation time + issuer (x/crypto puts both there)."""
+    hashed = bytes([5, 2]) + struct.pack(">I", ctime) + bytes([9, 16]) + struct.pack(">Q", key_id)
+    head = bytes([4, sig_type, 1, hash_id]) + struct.pack(">H", len(hashed)) + hashed
+    d = hashlib.new(_HASHLIB[hash_id], signed + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
+    return _new_packet(2, head + struct.pack(">H", 0) + d[:2] + _mpi(raw_rsa_sign(k, hash_id, d)))
+
+
+def make_transport_message(k, key_id: int, plain: bytes, nonce: bytes, ctime: int = 0x5F000000, hash_id: int = 8) -> bytes:
+    """The decrypted content of one bftkv transport message (Message.Encrypt, crypto_pgp.go:418-438)."""
+    import base64
+    return one_pass_packet(0, hash_id, 1, key_id) + go_literal_packet(plain, base64.b64encode(nonce)) + \
+        go_signature_packet(k, key_id, hash_id, plain, ctime)

@@ -43,6 +43,9 @@ extern "C" {
 #define BFTQ_ERR_INVALID_SIGNATURE -6   /* crypto.ErrInvalidSignature (crypto/crypto.go)         */
 #define BFTQ_ERR_INSUFFICIENT_SIGS -7   /* crypto.ErrInsufficientNumberOfSignatures              */
 #define BFTQ_ERR_MALFORMED         -8
+#define BFTQ_ERR_NOT_SIGNED        -9   /* crypto.ErrInvalidTransportSecurityData (crypto_pgp.go:458-460)  */
+#define BFTQ_ERR_MESSAGE_BODY     -10   /* the literal body ends early / FileName is not base64: Decrypt returns that error as is */
+#define BFTQ_ERR_UNSUPPORTED      -11   /* a form the reference's library handles and this build does not (compressed data)       */
 
 /* ---- per-item status bytes (SURVEY §8b "Errors") --------------------------------------------
  * The reference collapses every failure to ErrInvalidSignature (crypto_pgp.go:325-327); the shim
@@ -363,12 +366,36 @@ int bftq_signature_plan_measure(bftq_keyring* kr, const uint8_t* tbs_blob, const
  * issuers present in the keyring (primary ids via getCertById), duplicates kept, in packet order. */
 int bftq_signature_signers(bftq_keyring* kr, const uint8_t* sig, uint64_t sig_len, uint64_t* out_ids, uint32_t cap, uint32_t* n);
 
+/* PGPMessage.Decrypt's signature half (crypto_pgp.go:453-471; the per-response check of every multicast,
+ * transport/transport.go:116-126), batched.  Item i is the packet stream the message's SymmetricallyEncrypted packet
+ * decrypts to — [compressed] one-pass signature, literal data, signature — the host keeps the private-key operation and
+ * the AES-CFB / MDC layer.  openpgp.ReadMessage's readSignedMessage + signatureCheckReader are restated packet for
+ * packet (old / new framing, partial-length literal bodies as Go's own writer emits them, v3 and v4 signatures, text
+ * mode): the literal body is hashed with the ONE-PASS packet's algorithm and signature type, the packet behind it is
+ * verified with the FIRST key KeysByIdUsage(one-pass key id, sign) yields, and a message whose signer is not in the
+ * keyring is NOT an error (m.SignedBy == nil: SignatureError stays nil, the reference returns peer = nil).
+ *   out_err[i]        0 | BFTQ_ERR_INVALID_SIGNATURE (m.SignatureError != nil) | BFTQ_ERR_MALFORMED (ReadMessage failed:
+ *                     crypto.ErrDecryptionFailed) | BFTQ_ERR_NOT_SIGNED | BFTQ_ERR_MESSAGE_BODY | BFTQ_ERR_UNSUPPORTED,
+ *                     in the precedence Decrypt applies them
+ *   out_signed_by[i]  m.SignedByKeyId (the shim maps it with GetCertById: the peer may be nil)
+ *   out_flags[i]      BFTQ_MSG_SIGNER_KNOWN (m.SignedBy != nil) | BFTQ_MSG_BINARY (literal format 'b')
+ *   out_plain_blob    (nullable) item i's plain text — the de-chunked literal body — at out_plain_blob + msg_off[i],
+ *                     out_plain_len[i] bytes: the blob needs msg_off[n_items] bytes, a plain text is never longer than its
+ *                     message
+ *   out_nonce_blob    (nullable) base64-decoded FileName likewise at out_nonce_blob + msg_off[i], out_nonce_len[i] bytes */
+#define BFTQ_MSG_SIGNER_KNOWN 0x01
+#define BFTQ_MSG_BINARY       0x02
+int bftq_message_verify_batch(bftq_keyring* kr, const uint8_t* msg_blob, const uint64_t* msg_off, uint64_t n_items, int32_t* out_err,
+                              uint64_t* out_signed_by, uint8_t* out_flags, uint8_t* out_plain_blob, uint32_t* out_plain_len,
+                              uint8_t* out_nonce_blob, uint32_t* out_nonce_len);
+
 /* Batching aggregator: bftkv calls Signature.Verify one (tbs, sig) at a time from many goroutines
  * (one per peer in transport.Multicast, transport/transport.go:110-127; one per HTTP request on the
  * servers).  bftq_aggregator_verify blocks its caller until the batch it was coalesced into has been
  * verified: a batch is flushed when it reaches max_batch items or max_wait_us after its first item.
  * This is where "tens of thousands of tuples" come from without touching bftkv's call sites.
- * cert / cert_len may be NULL / 0 (Verify) or carry the issuer's key block (VerifyWithCertificate).
+ * cert == NULL selects Verify; a non-NULL cert selects VerifyWithCertificate with that key block — also when cert_len is 0
+ * (an empty certificate fails, it never falls back to the shared keyring).
  * Returns 0 (valid), BFTQ_ERR_INVALID_SIGNATURE, or a BFTQ_ERR_* infrastructure error. */
 typedef struct bftq_aggregator bftq_aggregator;
 int  bftq_aggregator_create(bftq_keyring* kr, uint32_t max_batch, uint32_t max_wait_us, bftq_aggregator** out);

@@ -664,3 +664,163 @@ def collective_combine(keyring: List[Entity], ss_type: int, ss_data: bytes, s_ty
     ss_data = (ss_data or b"") + (s_data or b"")
     ids = signers(keyring, ss_data)
     return quorum.is_sufficient([Node(i) for i in ids]), ss_type, ss_data
+
+
+# ---- transport messages: PGPMessage.Decrypt's signature half --------------------------------------------------
+# crypto/pgp/crypto_pgp.go:453-471 -> openpgp.ReadMessage -> readSignedMessage + signatureCheckReader
+# (golang.org/x/crypto/openpgp/read.go @53104e6ec876, restated from the published module; its source is not in the
+# reference tree).  The input here is what the SymmetricallyEncrypted packet decrypts to — the host keeps the RSA
+# private-key operation and the AES-CFB/MDC layer — i.e. the packet stream
+#     [compressed]  one-pass signature (tag 4)   literal data (tag 11)   signature (tag 2)
+
+ERR_DECRYPTION_FAILED = "crypto: decryption failed"                              # ReadMessage returned an error
+ERR_TRANSPORT_SECURITY = "crypto: invalid transport security data"                # !(IsEncrypted && IsSigned)
+ERR_MESSAGE_BODY = "message body / nonce error"                                   # ioutil.ReadAll or base64 error, returned as is
+ERR_MESSAGE_UNSUPPORTED = "unsupported message form (compressed data)"            # NOT restated: the reference would inflate and go on
+
+
+@dataclass
+class MessageResult:
+    err: Optional[str] = None
+    plain: Optional[bytes] = None
+    nonce: Optional[bytes] = None
+    signed_by_key_id: int = 0
+    signer_known: bool = False          # md.SignedBy != nil
+
+
+_B64 = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/"
+
+
+def go_base64_std_decode(src: bytes) -> Optional[bytes]:
+    """encoding/base64 StdEncoding.DecodeString (Go 1.13): CR and LF are skipped anywhere, every other byte outside the
+    alphabet is an error, padding is mandatory ('xx==' / 'xxx=' close the input: only CR / LF may follow), trailing bits
+    are not checked.  None = CorruptInputError."""
+    out = bytearray()
+    chars = [c for c in src if c not in (0x0D, 0x0A)]
+    i, n = 0, len(chars)
+    while i < n:
+        quad = chars[i:i + 4]
+        i += 4
+        vals = []
+        for j, c in enumerate(quad):
+            if c == 0x3D:                                  # '='
+                if j < 2:
+                    return None
+                if j == 2 and (len(quad) < 4 or quad[3] != 0x3D):
+                    return None
+                if i < n:                                  # data after the padding
+                    return None
+                break
+            k = _B64.find(bytes([c]))
+            if k < 0:
+                return None
+            vals.append(k)
+        else:
+            if len(quad) < 4:
+                return None                                # incomplete quantum without padding
+        if len(vals) == 4:
+            out += bytes([(vals[0] << 2) | (vals[1] >> 4), ((vals[1] & 15) << 4) | (vals[2] >> 2), ((vals[2] & 3) << 6) | vals[3]])
+        elif len(vals) == 3:
+            out += bytes([(vals[0] << 2) | (vals[1] >> 4), ((vals[1] & 15) << 4) | (vals[2] >> 2)])
+        elif len(vals) == 2:
+            out += bytes([(vals[0] << 2) | (vals[1] >> 4)])
+        else:
+            return None
+    return bytes(out)
+
+
+def message_verify(keyring: List[Entity], stream: bytes) -> MessageResult:
+    """PGPMessage.Decrypt on the decrypted packet stream.  Mirrors, in order:
+      readSignedMessage's FindLiteralData loop  (compressed -> unsupported here; one-pass signature: must be IsLast,
+        hashForSignature(p.Hash, p.SigType) must succeed, IsSigned = true, SignedBy = first key of
+        KeysByIdUsage(KeyId, KeyFlagSign); the LAST one-pass packet before the literal wins)
+      Decrypt's `!(m.IsEncrypted && m.IsSigned)` check
+      ioutil.ReadAll(m.UnverifiedBody): with a known signer the packet after the literal data is read at EOF and
+        verified with SignedBy.PublicKey.VerifySignature / VerifySignatureV3 over a hash made with the ONE-PASS packet's
+        algorithm and signature type; with an unknown signer NOTHING after the literal is looked at and SignatureError
+        stays nil (the reference then returns peer = nil, err = nil)
+      base64.StdEncoding.DecodeString(FileName)
+    """
+    res = MessageResult()
+    r = Reader(stream or b"")
+    ops = None
+    lit = None
+    try:
+        while True:
+            at_literal = r.pos < len(r.data) and r.data[r.pos] & 0x80 and ((r.data[r.pos] & 0x3F) if r.data[r.pos] & 0x40 else ((r.data[r.pos] & 0x3F) >> 2)) == 11
+            try:
+                pk = read_packet(r)
+            except PGPError:
+                if at_literal:          # the literal body ends early: ioutil.ReadAll's error, after the IsSigned check
+                    res.err = ERR_MESSAGE_BODY if ops is not None else ERR_TRANSPORT_SECURITY
+                    return res
+                raise
+            if pk is None:
+                raise StructuralError("EOF before literal data")          # packets.Next() -> io.EOF -> ReadMessage fails
+            tag, body = pk
+            if tag not in KNOWN_TAGS:
+                continue
+            if tag == 8:
+                res.err = ERR_MESSAGE_UNSUPPORTED
+                return res
+            if tag == 4:
+                if len(body) < 13:
+                    raise StructuralError("short one-pass signature")
+                if body[0] != 3:
+                    raise UnsupportedError("one-pass-signature packet version")
+                if body[2] not in HASH_BY_ID:
+                    raise UnsupportedError("hash function")
+                if not body[12]:
+                    raise UnsupportedError("nested signatures")
+                if body[2] == 3:
+                    raise UnsupportedError("hash not available")           # crypto.RIPEMD160 is not linked into bftkv
+                if body[1] not in (0x00, 0x01):
+                    raise UnsupportedError("unsupported signature type")
+                ops = {"sig_type": body[1], "hash_id": body[2], "pk_algo": body[3], "key_id": int.from_bytes(body[4:12], "big")}
+            elif tag == 2:
+                parse_signature(body)                                       # parsed by packet.Read, ignored by the switch
+            elif tag == 11:
+                if len(body) < 2 or len(body) < 2 + body[1] + 4:
+                    raise StructuralError("short literal data")
+                nl = body[1]
+                lit = {"binary": body[0] == ord("b"), "name": body[2:2 + nl], "body": body[6 + nl:]}
+                break
+    except PGPError:
+        res.err = ERR_DECRYPTION_FAILED
+        return res
+    if ops is None:
+        res.err = ERR_TRANSPORT_SECURITY
+        return res
+    res.signed_by_key_id = ops["key_id"]
+    keys = keys_by_id_usage(keyring, ops["key_id"], KEY_FLAG_SIGN)
+    res.signer_known = bool(keys)
+    sig_err = None
+    if keys:
+        try:
+            while True:                                                     # packets.Next(): unknown types are skipped
+                pk = read_packet(r)
+                if pk is None:
+                    raise StructuralError("EOF")
+                if pk[0] in KNOWN_TAGS:
+                    break
+            if pk[0] != 2:
+                raise StructuralError("LiteralData not followed by signature")
+            sig = parse_signature(pk[1])
+            # the hash object was made from the one-pass packet: its algorithm digests, its type canonicalises
+            import copy
+            fake = copy.copy(sig)
+            fake.sig_type = ops["sig_type"]
+            if ops["hash_id"] != sig.hash_id:
+                if hashlib.new(HASH_BY_ID[ops["hash_id"]]).digest_size != hashlib.new(HASH_BY_ID[sig.hash_id]).digest_size:
+                    raise SignatureError("digest made with the one-pass hash does not fit the signature's hash")
+                raise UnsupportedError("oracle: same-length digest under another algorithm's DigestInfo not restated")
+            verify_signature(keys[0].public_key, lit["body"], fake)
+        except PGPError as ex:
+            sig_err = ex
+    nonce = go_base64_std_decode(lit["name"])
+    if nonce is None:
+        res.err = ERR_MESSAGE_BODY
+        return res
+    res.plain, res.nonce = lit["body"], nonce
+    res.err = ERR_INVALID_SIGNATURE if sig_err is not None else None
+    return res
