@@ -487,6 +487,52 @@ def run_gpu(args, rank, local_rank, world):
     eng5.close()
     del ro5, pool5
 
+    # ---- quorum-certified read ops from RAW ANSWERS: packets in, decisions out ------------------------------------------------
+    # BASELINE configs[2]'s shape (16-replica quorum) in the form Client.Read receives it: every answer is the decrypted
+    # transport message (one-pass signature, partial-length literal data whose FileName carries the nonce, signature) around
+    # the replica's stored packet <x, v, t, sig, ss> with an 11-signature collective signature — about 3.9 kB per answer.
+    # One bftq_read_responses_batch call per step: H2D of the raw answers, K0m (parse, de-chunk, nonce check, packet.Parse,
+    # SHA-256 of the body, hash-tag check), K1, K2m (values compared byte for byte, arrival-order decision), D2H.
+    from bftkv_b200.crypto_gpu import read_responses_batch
+    R6, M6 = 16, args.ops6
+    ra = workload.make_read_answers(M6, R6, seed=0xBF7C0007 + rank, mix=workload.HARD_MIX)
+    eng6 = Engine(local_rank)
+    eng6.bind_thread()
+    kr6 = Keyring(eng6)
+    kr6.register(ra["keyring"])
+    qcs6 = [(5, 16, 6, 11, ra["ids"])]
+    blob6, off6 = _blob(ra["msgs"])
+    pin6 = (eng6.host_copy(blob6), eng6.host_copy(off6))
+    N6 = M6 * R6
+
+    def q6step():
+        return read_responses_batch(kr6, qcs6, ra["op_off"], ra["peer_ids"], None, ra["nonces"], pre_status=ra["pre_status"], blobs=pin6)
+    q6step()
+    s60 = eng6.stats()
+    q6steps = max(2, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(q6steps):
+        got6 = q6step()
+    q6_s = time.perf_counter() - t0
+    barrier()
+    s61 = eng6.stats()
+    assert np.array_equal(got6["status"] != 0, ra["expect_status"] != 0), "raw-answer statuses differ from expectation"
+    if rank == 0:
+        from oracle import c_oracle
+        rd, rw, ra_ = c_oracle.read_decide_batch([(5, 16, 6, 11, list(range(16)))], ra["op_off"], ra["key_idx"].astype(np.uint64), ra["expect_status"],
+                                                 ra["ts"], ra["value_id"])
+        assert np.array_equal(got6["decision"], rd) and np.array_equal(got6["winner"], rw) and np.array_equal(got6["decided_at"], ra_), \
+            "raw-answer decisions differ from the oracle"
+    q6_info = {"bytes_per_answer": int(off6[-1]) // max(1, int((ra["pre_status"] == 0).sum())), "h2d_bytes_per_step": (s61["h2d_bytes"] - s60["h2d_bytes"]) // q6steps,
+               "gpu_parsed": (s61["msg_gpu_items"] - s60["msg_gpu_items"]) // q6steps, "host_parsed": (s61["msg_host_items"] - s60["msg_host_items"]) // q6steps,
+               "decisions": {k: int((got6["decision"] == v).sum()) for k, v in (("value", 0), ("rejected", 1), ("exhausted", 2))}}
+    kr6.close()
+    for a in pin6:
+        eng6.host_free(a)
+    eng6.close()
+    del ra, blob6
+
     # ---- secondary: BASELINE configs[3] — 262144 Ed25519 verifies (K = 15 keys) + Lagrange combines ----
     # (the reference itself cannot verify Ed25519; reported for completeness of the configs)
     ed = None
@@ -570,10 +616,10 @@ def run_gpu(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, q_ms, pgp_s * 1e3, sus_ms / n_sus, pgp_sus_s * 1e3 / n_e2e_sus, q5_s * 1e3, pgp_pageable_s * 1e3,
-                      pgp_info["thread_ms"]["stage"], pgp_info["thread_ms"]["wait"]], dtype=torch.float64, device=dev)
+                      pgp_info["thread_ms"]["stage"], pgp_info["thread_ms"]["wait"], q6_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, q_ms, pgp_ms, sus_ms_step, pgp_sus_ms_step, q5_ms, pgp_pageable_ms, stage_ms_max, wait_ms_max = [float(x) for x in t]
+    dev_ms, e2e_ms, q_ms, pgp_ms, sus_ms_step, pgp_sus_ms_step, q5_ms, pgp_pageable_ms, stage_ms_max, wait_ms_max, q6_ms = [float(x) for x in t]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -641,7 +687,19 @@ def run_gpu(args, rank, local_rank, world):
                                           "responses": "per-op mix: 80% as SURVEY config 3 (0.90 ok / 0.05 stale / 0.03 bad / 0.02 missing), 20% degraded classes "
                                                        "(workload.HARD_MIX); responses arrive in seeded random order",
                                           "decisions_rank0": dec_hist, "checked": "statuses vs expectation on every rank; decisions vs the C oracle on rank 0",
-                                          "data": "synthetic; tuples drawn from a pool of %d genuine signatures over 31 keys" % args.pool5}}},
+                                          "data": "synthetic; tuples drawn from a pool of %d genuine signatures over 31 keys" % args.pool5}},
+                       "e2e_packets": {"metric": "quorum_certified_read_ops_per_sec", "value": M6 * world * q6steps / (q6_ms * 1e-3), "unit": "ops/s",
+                                       "answers_per_sec": N6 * world * q6steps / (q6_ms * 1e-3), "steps": q6steps, "ms_per_step": q6_ms / q6steps,
+                                       "h2d_bytes_per_step": int(q6_info["h2d_bytes_per_step"]), "bytes_per_answer": q6_info["bytes_per_answer"],
+                                       "h2d_gbps_achieved": q6_info["h2d_bytes_per_step"] * q6steps / (q6_ms * 1e-3) / 1e9,
+                                       "api": "bftq_read_responses_batch: the decrypted transport answers (one-pass signature, partial-length literal data, signature) in "
+                                              "page-locked host memory in, per-answer status + per-op Client.Read decision out; message parsing, de-chunking, nonce check, "
+                                              "packet.Parse, SHA-256, RSA verify and the tally all on the GPU",
+                                       "config": {"workload": "%d read ops x 16-replica quorum per GPU, every answer a ~3.9 kB transport message around the stored packet "
+                                                              "<x, v, t, sig, ss(11 signatures)>; response mix workload.HARD_MIX, random arrival order" % M6,
+                                                  "answers_parsed_on_gpu_rank0": int(q6_info["gpu_parsed"]), "answers_through_host_packer_rank0": int(q6_info["host_parsed"]),
+                                                  "decisions_rank0": q6_info["decisions"], "checked": "statuses vs expectation on every rank; decisions vs the C oracle on rank 0",
+                                                  "data": "synthetic; one signed template per (replica, current / stale value), the nonce in the unsigned FileName differs per answer"}}},
         "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE on the FMA-heavy pipe)",
                      "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rsa_verify_r32_kernel launch (65536 items) in "
@@ -710,6 +768,7 @@ def main():
     ap.add_argument("--pgp-callers", type=int, default=2, help="concurrent host callers in the packet-level end-to-end leg")
     ap.add_argument("--sustain", type=float, default=2.2, help="seconds of the sustained legs")
     ap.add_argument("--pool5", type=int, default=32768, help="genuine signatures in the configs[4] pool")
+    ap.add_argument("--ops6", type=int, default=8192, help="read operations per GPU in the raw-answer leg")
     ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

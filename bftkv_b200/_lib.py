@@ -17,7 +17,8 @@ class Stats(C.Structure):
     _fields_ = [("items", C.c_uint64), ("launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("packer_chunks", C.c_uint64),
                 ("packer_parse_ns", C.c_uint64), ("packer_stage_ns", C.c_uint64), ("packer_wait_ns", C.c_uint64),
-                ("numa_node", C.c_int32), ("numa_cpus", C.c_uint32)]
+                ("numa_node", C.c_int32), ("numa_cpus", C.c_uint32), ("msg_gpu_items", C.c_uint64), ("msg_host_items", C.c_uint64),
+                ("unsupported_items", C.c_uint64)]
 
 
 _lib = None
@@ -83,6 +84,7 @@ def load():
         "bftq_signature_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_signature_verify_with_cert_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp]),
         "bftq_message_verify_batch": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]),
+        "bftq_read_responses_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
         "bftq_signature_signers": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u32p]),
         "bftq_aggregator_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
         "bftq_aggregator_destroy": (None, [vp]),

@@ -319,3 +319,34 @@ class Message:
 
     def decrypt_verify(self, stream: bytes):
         return self.decrypt_verify_batch([stream])[0]
+
+
+def read_responses_batch(kr: "Keyring", qcs, op_off, peer_ids, msgs: Sequence[bytes], nonces, pre_status=None, blobs=None):
+    """Client.Read from raw answers (bftq_read_responses_batch).  qcs: [(f, min, threshold, suff, [node ids])]; op_off (n_ops+1)
+    uint32; peer_ids (N) uint64; msgs: N decrypted answers; nonces (N, nonce_len) uint8 — the nonces the requests carried.
+    blobs: (msg_blob, msg_off) arrays to use instead of joining `msgs` (e.g. page-locked ones).
+    Returns dict(status, ts, value_off, value_len, decision, winner, decided_at)."""
+    op_off = np.ascontiguousarray(op_off, np.uint32)
+    n_ops, n = len(op_off) - 1, int(op_off[-1])
+    arr = (QCIds * max(1, len(qcs)))()
+    members, off = [], 0
+    for i, (f, mn, th, sf, m) in enumerate(qcs):
+        arr[i] = QCIds(f, mn, th, sf, off, len(m))
+        members += list(m)
+        off += len(m)
+    mem = np.asarray(members if members else [0], np.uint64)
+    blob, moff = blobs if blobs is not None else _blob(msgs)
+    peer_ids = np.ascontiguousarray(peer_ids, np.uint64)
+    nonces = np.ascontiguousarray(nonces, np.uint8)
+    nonce_len = int(nonces.shape[1])
+    pre = None if pre_status is None else np.ascontiguousarray(pre_status, np.uint8)
+    out = {"status": np.zeros(max(n, 1), np.uint8), "ts": np.zeros(max(n, 1), np.uint64), "value_off": np.zeros(max(n, 1), np.uint32),
+           "value_len": np.zeros(max(n, 1), np.uint32), "decision": np.zeros(n_ops, np.uint8), "winner": np.zeros(n_ops, np.uint32),
+           "decided_at": np.zeros(n_ops, np.uint32)}
+    p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+    _lib.check(kr._lib.bftq_read_responses_batch(kr._h, C.cast(arr, C.c_void_p), len(qcs), p(mem), len(members), p(op_off), n_ops, p(peer_ids), p(blob), p(moff),
+                                                 p(pre), p(nonces), nonce_len, p(out["status"]), p(out["ts"]), p(out["value_off"]), p(out["value_len"]),
+                                                 p(out["decision"]), p(out["winner"]), p(out["decided_at"])))
+    for k in ("status", "ts", "value_off", "value_len"):
+        out[k] = out[k][:n]
+    return out

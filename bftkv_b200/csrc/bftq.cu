@@ -12,6 +12,7 @@
 #include "dsa_verify.cuh"
 #include "pgp_digest.cuh"
 #include "pgp_parse.cuh"
+#include "msg_parse.cuh"
 #include "pgp_host.hpp"
 #include "wotqs_host.hpp"
 

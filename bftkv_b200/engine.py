@@ -324,7 +324,8 @@ class Engine:
         _lib.check(self._lib.bftq_stats(self._h, C.byref(s)))
         return {"items": s.items, "launches": s.launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes,
                 "packer_chunks": s.packer_chunks, "packer_parse_ns": s.packer_parse_ns, "packer_stage_ns": s.packer_stage_ns,
-                "packer_wait_ns": s.packer_wait_ns, "numa_node": s.numa_node, "numa_cpus": s.numa_cpus}
+                "packer_wait_ns": s.packer_wait_ns, "numa_node": s.numa_node, "numa_cpus": s.numa_cpus,
+                "msg_gpu_items": s.msg_gpu_items, "msg_host_items": s.msg_host_items, "unsupported_items": s.unsupported_items}
 
     def measure_int_peak(self) -> float:
         v = C.c_double()

@@ -326,3 +326,71 @@ def make_transport_message(k, key_id: int, plain: bytes, nonce: bytes, ctime: in
     import base64
     return one_pass_packet(0, hash_id, 1, key_id) + go_literal_packet(plain, base64.b64encode(nonce)) + \
         go_signature_packet(k, key_id, hash_id, plain, ctime)
+
+
+def make_read_answers(n_ops: int, n_replicas: int, seed: int = 0xBF7C0007, ss_signers: int = 11, p_ok=0.90, p_stale=0.05, p_bad=0.03,
+                      mix=None, shuffle_arrival=True):
+    """Configs 3 / 5 in the form Client.Read receives them: for every (operation, replica) the decrypted transport
+    answer — one-pass signature, literal data (FileName = base64(nonce)), signature, as Message.Encrypt writes them —
+    whose plain text is the replica's stored packet packet.Serialize(x, v, t, sig, ss): x 16 B, v 32 B, the writer's
+    signature (one OpenPGP packet) and a collective signature of `ss_signers` packets (suff = 11 for n = 16), about
+    4 kB per answer.  The transport signature covers the literal BODY only, so one signed template per (replica, current /
+    stale) serves every operation and only the nonce in the FileName differs per answer; a corrupted answer has one bit
+    of its signature MPI flipped; a missing one is flagged in pre_status.
+    Returns dict(keyring, ids, op_off, peer_ids, msgs (list of bytes), nonces (N, 8), pre_status, expect_status, ts, value_len)."""
+    import base64
+    from oracle import packet_oracle as pk          # only MAKES inputs (byte layout of packet.Serialize), never verifies
+    rng = np.random.default_rng(seed)
+    R, M = n_replicas, n_ops
+    keys = load_keys(R)
+    blocks, kids = [], []
+    for i, k in enumerate(keys):
+        b, kid = pgp_public_key_block(k, _private_key(k), b"a%02d (http://localhost:57%02d) <a%02d@bftq.test>" % (i, i, i))
+        blocks.append(b); kids.append(kid)
+    x = bytes(range(16))
+    vals = {0: (bytes(rng.integers(0, 256, 32, dtype=np.uint8)), 7), 1: (bytes(rng.integers(0, 256, 32, dtype=np.uint8)), 6)}
+    templates = {}
+    for kind, (v, t) in vals.items():
+        tbs = tbs_packet(x, v, t)
+        wsig = sig_packet_v4(keys[0], kids[0], 8, tbs, 0x5F000001)
+        ss = b"".join(sig_packet_v4(keys[j % R], kids[j % R], 8, tbs, 0x5F000002) for j in range(ss_signers))
+        plain = pk.serialize(x, v, t, pk.SignaturePacket(type=1, version=1, completed=False, data=wsig, cert=b""),
+                             pk.SignaturePacket(type=1, version=1, completed=True, data=ss, cert=b""))
+        for r in range(R):
+            m = make_transport_message(keys[r], kids[r], plain, b"\x00" * 8)
+            # the 12 FileName characters: an 8-byte and a 4-byte partial chunk right after the 2-byte literal header chunk
+            p0 = 15 + 1 + 1 + 2 + 1                      # one-pass (15) | CB | E1 | 'b' len | E3
+            assert m[15] == 0xCB and m[16] == 0xE1 and m[19] == 0xE3 and m[28] == 0xE2
+            templates[(kind, r)] = (bytearray(m), p0, p0 + 9)
+    N = M * R
+    key_idx = np.tile(np.arange(R, dtype=np.uint32), M)
+    if shuffle_arrival:
+        key_idx = rng.permuted(key_idx.reshape(M, R), axis=1).reshape(N).astype(np.uint32)
+    u = rng.random(N)
+    if mix is None:
+        pk_, ps, pb = p_ok, p_stale, p_bad
+    else:
+        cls = rng.choice(len(mix), size=M, p=[m[0] for m in mix])
+        pk_ = np.repeat(np.array([m[1] for m in mix])[cls], R)
+        ps = np.repeat(np.array([m[2] for m in mix])[cls], R)
+        pb = np.repeat(np.array([m[3] for m in mix])[cls], R)
+    kind = np.where(u < pk_, 0, np.where(u < pk_ + ps, 1, np.where(u < pk_ + ps + pb, 2, 3)))
+    nonces = rng.integers(0, 256, (N, 8), dtype=np.uint8)
+    flip = rng.integers(8, 200, N)
+    msgs = []
+    for i in range(N):
+        tpl, a, b = templates[(1 if kind[i] == 1 else 0, int(key_idx[i]))]
+        m = bytearray(tpl)
+        n64 = base64.b64encode(nonces[i].tobytes())
+        m[a:a + 8] = n64[:8]
+        m[b:b + 4] = n64[8:]
+        if kind[i] == 2:
+            m[len(m) - int(flip[i])] ^= 0x10                      # inside the signature MPI
+        msgs.append(bytes(m) if kind[i] != 3 else b"")
+    pre = np.where(kind == 3, 6, 0).astype(np.uint8)
+    expect = np.where(kind == 2, 1, pre).astype(np.uint8)
+    ts = np.where(kind == 1, 6, 7).astype(np.uint64)
+    op_off = (np.arange(M + 1, dtype=np.uint64) * R).astype(np.uint32)
+    return {"keyring": b"".join(blocks), "ids": kids, "op_off": op_off, "peer_ids": np.array(kids, np.uint64)[key_idx], "msgs": msgs,
+            "nonces": nonces, "pre_status": pre, "expect_status": expect, "ts": ts, "value_id": np.where(kind == 1, 1, 0).astype(np.uint32),
+            "key_idx": key_idx}

@@ -57,6 +57,9 @@ extern "C" {
 #define BFTQ_ST_UNKNOWN_SIGNER  4   /* key index out of range / issuer not in keyring            */
 #define BFTQ_ST_UNSUPPORTED     5   /* algorithm the reference's library cannot verify either    */
 #define BFTQ_ST_MISSING         6   /* no response from this replica (tally input only)          */
+#define BFTQ_ST_NONCE_MISMATCH  7   /* transport.ErrTransportNonceMismatch (transport.go:121-124)  */
+#define BFTQ_ST_UNVERIFIED_SIGNER 8 /* ACCEPTED, as the reference accepts it: the message's signer is not in the keyring, so
+                                       openpgp.ReadMessage leaves SignedBy nil and never checks the signature (read path only) */
 
 /* ---- hash algorithm ids = OpenPGP ids (RFC 4880 §9.4), as sig.Hash in x/crypto ---------------*/
 #define BFTQ_HASH_MD5        1
@@ -431,6 +434,26 @@ int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uin
 int bftq_collective_combine_sufficient(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
                                        uint32_t n_members, const uint8_t* ss, uint64_t ss_len, int32_t* out);
 
+/* The read path from raw answers: what Client.Read (protocol/client.go:250-268) does with the R answers of each of n_ops
+ * read operations, once the host has removed the encryption layer of every answer — packets in, decisions out.
+ * Response p (operation i owns [op_off[i], op_off[i+1]), in ARRIVAL order, at most 32) is
+ *   peer_ids[p]     the node the request went to (res.Peer: what the quorum predicates count; the message's signer is NOT
+ *                   compared with it — transport.Multicast ignores Decrypt's peer, transport/transport.go:119)
+ *   msg p           the packet stream its answer decrypts to (as bftq_message_verify_batch takes it)
+ *   pre_status[p]   (nullable) non-zero: the transport failed earlier (no answer, HTTP error, decryption failed) — a failure
+ *   nonce p         nonce_len bytes at nonce_blob + p * nonce_len: the nonce the request carried (transport.go:103,121)
+ * Per response: Message.Decrypt's signature half, then the nonce comparison, then packet.Parse of a non-empty answer
+ * (client.go:207-230; an empty answer buckets as ("", 0)); per operation: the arrival-order decision of
+ * bftq_read_decide_batch, values compared byte for byte.  K0m parses, de-chunks, hashes and lays out K1's inputs on the
+ * GPU for the shape every bftkv answer has; anything else goes through the host packer and is patched in.
+ *   out_status[p]     BFTQ_ST_OK / BFTQ_ST_UNVERIFIED_SIGNER (both count as good answers) or the failure kind
+ *   out_ts / out_value_off / out_value_len (nullable)  timestamp and value span inside the answer's plain text
+ *   out_decision / out_winner / out_decided_at          as bftq_read_decide_batch */
+int bftq_read_responses_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids, uint32_t n_members,
+                              const uint32_t* op_off, uint64_t n_ops, const uint64_t* peer_ids, const uint8_t* msg_blob, const uint64_t* msg_off,
+                              const uint8_t* pre_status, const uint8_t* nonce_blob, uint32_t nonce_len, uint8_t* out_status, uint64_t* out_ts,
+                              uint32_t* out_value_off, uint32_t* out_value_len, uint8_t* out_decision, uint32_t* out_winner, uint32_t* out_decided_at);
+
 /* ---- quorum-descriptor builder (host only; no GPU needed) --------------------------------------
  * The step before the tally: wotqs.ChooseQuorum over the PGP trust graph
  * (quorum/wotqs/wotqs.go:36-127, node/graph/graph.go:46-75,117-125,279-393,420-438).  The shim
@@ -469,6 +492,10 @@ typedef struct {
   uint64_t packer_wait_ns;   /* waiting for a chunk's results                                          */
   int32_t  numa_node;        /* NUMA node of the engine's GPU (-1 unknown)                             */
   uint32_t numa_cpus;        /* CPUs the library's worker threads are bound to (0 = not bound)         */
+  uint64_t msg_gpu_items;    /* transport answers parsed + hashed on the GPU (K0m) by bftq_read_responses_batch   */
+  uint64_t msg_host_items;   /* ... and the ones K0m flagged, decided through the host packer                    */
+  uint64_t unsupported_items;/* tuples answered BFTQ_ST_UNSUPPORTED by the packer: algorithms / key sizes the
+                                reference's library can verify and this build cannot (INTEGRATION.md "fallback") */
 } bftq_stats_t;
 int bftq_stats(bftq_engine* e, bftq_stats_t* out);
 

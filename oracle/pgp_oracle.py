@@ -824,3 +824,32 @@ def message_verify(keyring: List[Entity], stream: bytes) -> MessageResult:
     res.plain, res.nonce = lit["body"], nonce
     res.err = ERR_INVALID_SIGNATURE if sig_err is not None else None
     return res
+
+
+# ---- Client.Read from raw answers (protocol/client.go:250-268 over transport.Multicast's per-response work) -------------
+ST_OK, ST_INVALID, ST_OTHER, ST_NONCE, ST_UNVERIFIED = 0, 1, 3, 7, 8
+
+
+def read_response_status(keyring: List[Entity], msg: bytes, nonce: bytes, pre: int = 0):
+    """One answer as transport.Multicast + Client.processResponse see it -> (status class, t, value bytes).
+    status: ST_OK / ST_UNVERIFIED (good answers: err == nil all the way), ST_INVALID (m.SignatureError), ST_NONCE
+    (ErrTransportNonceMismatch, transport.go:121-124), ST_OTHER (every other error: ReadMessage, missing one-pass packet,
+    body / base64 errors, packet.Parse, or `pre`: the transport failed earlier)."""
+    from . import packet_oracle
+    if pre:
+        return ST_OTHER, 0, b""
+    r = message_verify(keyring, msg)
+    if r.err == ERR_INVALID_SIGNATURE:
+        return ST_INVALID, 0, b""
+    if r.err is not None:
+        return ST_OTHER, 0, b""
+    if r.nonce != nonce:
+        return ST_NONCE, 0, b""
+    t, value = 0, b""
+    if r.plain:                                                    # processResponse: `if res.Data != nil && len(res.Data) > 0`
+        try:
+            _, value, t, _, _, _ = packet_oracle.parse(r.plain)
+        except (EOFError, ValueError):
+            return ST_OTHER, 0, b""
+        value = value or b""
+    return (ST_OK if r.signer_known else ST_UNVERIFIED), t, value
