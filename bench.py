@@ -395,6 +395,59 @@ def run_gpu(args, rank, local_rank, world):
     for a in pin:
         eng.host_free(a)
 
+    # ---- server-side write path: CollectiveSignature.Verify's batch form (crypto_pgp.go:485-500, protocol/server.go:300) ---------
+    # Each item: one TBSS string and a collective signature of 11 detached OpenPGP signature packets by members of a
+    # 16-node clique (n = 16: f = 5, suff = 11; 2 % of the packets corrupted, so some items fall below suff).  The host
+    # frames the packets (headers only), K0 parses + hashes every packet against its item's signed bytes, K1 verifies,
+    # K2 decides IsSufficient per item.  Signed templates: 8 TBSS variants x 16 keys; items draw from them.
+    from bftkv_b200.crypto_gpu import QCIds
+    NC, NSIG = args.coll_items, 11
+    crng = np.random.default_rng(0xBF7C0008 + rank)
+    ckeys = workload.load_keys(16)
+    cblocks, ckids = [], []
+    for i, k in enumerate(ckeys):
+        b_, kid_ = workload.pgp_public_key_block(k, workload._private_key(k), b"a%02d (http://localhost:57%02d) <a%02d@bftq.test>" % (i, i, i))
+        cblocks.append(b_); ckids.append(kid_)
+    ctbs = [workload.tbs_packet(bytes([j]) * 16, bytes([j + 1]) * 32, 1000 + j) for j in range(8)]
+    csig = [[workload.sig_packet_v4(ckeys[i], ckids[i], 8, ctbs[j], 0x5F000000 + i) for i in range(16)] for j in range(8)]
+    c_tbs, c_ss, c_expect = [], [], []
+    for it in range(NC):
+        j = int(crng.integers(0, 8))
+        mem = crng.permutation(16)[:NSIG]
+        parts, good = [], 0
+        for i in mem:
+            pkt = csig[j][int(i)]
+            if crng.random() < 0.02:
+                bb = bytearray(pkt); bb[-1 - int(crng.integers(0, 200))] ^= 0x04; pkt = bytes(bb)
+            else:
+                good += 1
+            parts.append(pkt)
+        c_tbs.append(ctbs[j]); c_ss.append(b"".join(parts)); c_expect.append(good >= 11)
+    krc = Keyring(eng)
+    krc.register(b"".join(cblocks))
+    ctb, cto = _blob(c_tbs)
+    csb, cso = _blob(c_ss)
+    cpin = [eng.host_copy(a) for a in (ctb, cto, csb, cso)]
+    carr = (QCIds * 1)(QCIds(5, 16, 11, 11, 0, 16))
+    cmem = np.asarray(ckids, np.uint64)
+    cerr = np.zeros(NC, np.int32)
+
+    def cstep():
+        L_.check(eng._lib.bftq_collective_verify_batch(krc._h, C.cast(carr, C.c_void_p), 1, vp(cmem), 16, vp(cpin[0]), vp(cpin[1]), vp(cpin[2]), vp(cpin[3]), NC, vp(cerr)))
+    cstep()
+    csteps = max(3, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(csteps):
+        cstep()
+    coll_s = time.perf_counter() - t0
+    barrier()
+    assert np.array_equal(cerr == 0, np.array(c_expect)), "collective results differ from expectation"
+    coll_accept = int((cerr == 0).sum())
+    krc.close()
+    for a in cpin:
+        eng.host_free(a)
+
     # ---- secondary: quorum-certified read ops (BASELINE configs[2]), device-resident ----------------------------
     # 65536 read ops x 16 replicas: verify every response + wotqs read tally (K1 + K2, one stream).
     # Signed tuples are drawn from this rank's 65536-signature pool (each slot gets a genuine
@@ -616,10 +669,10 @@ def run_gpu(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, q_ms, pgp_s * 1e3, sus_ms / n_sus, pgp_sus_s * 1e3 / n_e2e_sus, q5_s * 1e3, pgp_pageable_s * 1e3,
-                      pgp_info["thread_ms"]["stage"], pgp_info["thread_ms"]["wait"], q6_s * 1e3], dtype=torch.float64, device=dev)
+                      pgp_info["thread_ms"]["stage"], pgp_info["thread_ms"]["wait"], q6_s * 1e3, coll_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, q_ms, pgp_ms, sus_ms_step, pgp_sus_ms_step, q5_ms, pgp_pageable_ms, stage_ms_max, wait_ms_max, q6_ms = [float(x) for x in t]
+    dev_ms, e2e_ms, q_ms, pgp_ms, sus_ms_step, pgp_sus_ms_step, q5_ms, pgp_pageable_ms, stage_ms_max, wait_ms_max, q6_ms, coll_ms = [float(x) for x in t]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -669,6 +722,13 @@ def run_gpu(args, rank, local_rank, world):
                      "api": "bftq_rsa_verify_batch (flat tuples: key index, padded signature, precomputed digest; pinned host buffers), "
                             "%d concurrent callers" % NCALLERS,
                      "ms_per_step": e2e_ms / args.steps},
+        "collective": {"metric": "collective_signature_verifies_per_sec", "value": NC * world * csteps / (coll_ms * 1e-3), "unit": "collective verifies/s",
+                       "signature_verifies_per_sec": NC * NSIG * world * csteps / (coll_ms * 1e-3), "steps": csteps, "ms_per_step": coll_ms / csteps,
+                       "api": "bftq_collective_verify_batch = crypto.CollectiveSignature.Verify's batch form (crypto_pgp.go:485-500): TBSS strings + concatenated "
+                              "OpenPGP signature packets in page-locked host blobs in, nil / ErrInsufficientNumberOfSignatures out; packets framed on the host, "
+                              "K0 + K1 + K2 (IsSufficient) on the GPU",
+                       "config": {"workload": "%d collective signatures x 11 packets by members of a 16-node clique (f = 5, suff = 11), 2%% of the packets corrupted" % NC,
+                                  "accepted_rank0": coll_accept, "data": "synthetic; packets drawn from 8 x 16 genuine signatures"}},
         "quorum_ops": {"metric": "quorum_certified_read_ops_per_sec", "value": M * world * qsteps / (q_ms * 1e-3), "unit": "ops/s",
                        "verifies_per_sec": NQ * world * qsteps / (q_ms * 1e-3), "steps": qsteps, "ms_per_step": q_ms / qsteps,
                        "config": {"workload": "batch 65536 read ops x 16-replica quorum, verify + wotqs read tally (BASELINE configs[2]), device-resident",
@@ -769,6 +829,7 @@ def main():
     ap.add_argument("--sustain", type=float, default=2.2, help="seconds of the sustained legs")
     ap.add_argument("--pool5", type=int, default=32768, help="genuine signatures in the configs[4] pool")
     ap.add_argument("--ops6", type=int, default=8192, help="read operations per GPU in the raw-answer leg")
+    ap.add_argument("--coll-items", type=int, default=16384, help="collective signatures per step in the server-side leg")
     ap.add_argument("--skip-ed25519", action="store_true", help="skip the BASELINE configs[3] secondary measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -49,17 +49,24 @@ pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __
                         const uint8_t* __restrict__ sig_blob, const uint64_t* __restrict__ sig_off, const uint64_t sig_base, const uint32_t n_items,
                         const IssuerEntry* __restrict__ issuers, const uint32_t n_issuers,
                         uint32_t* __restrict__ out_key_idx, uint8_t* __restrict__ out_sig /* n x 256 */,
-                        uint8_t* __restrict__ out_digest /* n x 32 */, uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where) {
+                        uint8_t* __restrict__ out_digest /* n x 32 */, uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where,
+                        // collective form (all nullable): item s is ONE packet of a multi-signature stream — its signed bytes are
+                        // tbs number data_idx[s], its packet ends at sig_end[s] (not at the next item's start), and the signer the
+                        // quorum tally counts (the dense index of the issuer's entity) goes to out_signer[s]
+                        const uint32_t* __restrict__ data_idx = nullptr, const uint64_t* __restrict__ sig_end = nullptr,
+                        const uint32_t* __restrict__ hit_signer = nullptr, uint32_t* __restrict__ out_signer = nullptr) {
   const uint32_t item_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = item_raw < n_items;
   const uint32_t item = live ? item_raw : n_items - 1;        // idle lanes shadow the last item (the warp copies together)
   const int lane = threadIdx.x & 31;
   // offsets are the caller's own (relative to its whole blob): the chunk's blobs start at tbs_base / sig_base
-  const uint64_t s0 = tbs_off[item] - tbs_base, s1 = tbs_off[item + 1] - tbs_base, g0 = sig_off[item] - sig_base, g1 = sig_off[item + 1] - sig_base;
+  const uint32_t di = data_idx != nullptr ? data_idx[item] : item;
+  const uint64_t s0 = tbs_off[di] - tbs_base, s1 = tbs_off[di + 1] - tbs_base, g0 = sig_off[item] - sig_base,
+                 g1 = (sig_end != nullptr ? sig_end[item] : sig_off[item + 1]) - sig_base;
   const uint8_t* sg = sig_blob + g0;
   // ---- per item: parse, issuer lookup ---------------------------------------------------------------
   uint8_t where = kParseDecided, pre = 0;
-  uint32_t kidx = 0;
+  uint32_t kidx = 0, signer = 0xffffffffu;
   bool copy = false, hash = false;
   fastparse::FastSig f;
   f.mpi_off = 0; f.mpi_len = 0; f.hashed_off = 0; f.hashed_len = 0; f.tag = 0;
@@ -74,6 +81,7 @@ pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __
       if (en.kind != 0) where = kParseHost;
       else {
         kidx = en.key_idx;
+        if (hit_signer != nullptr) signer = hit_signer[hit];
         hash = true;
         if (en.algo != f.pk_algo) pre = 1;                                 // "public key and signature use different algorithms"
         if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }                  // len(sig) != k
@@ -130,7 +138,7 @@ pgp_parse_digest_kernel(const uint8_t* __restrict__ tbs_blob, const uint64_t* __
     for (int i = 0; i < 8; i++) o[i] = __byte_perm(h[i], 0, 0x0123);        // big-endian bytes
     if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;                   // BFTQ_ST_HASH_TAG
   }
-  if (live) { out_key_idx[item] = kidx; out_pre[item] = pre; out_where[item] = where; }
+  if (live) { out_key_idx[item] = kidx; out_pre[item] = pre; out_where[item] = where; if (out_signer != nullptr) out_signer[item] = signer; }
 }
 
 }  // namespace bftq

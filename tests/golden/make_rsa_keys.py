@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Deterministic RSA-2048 test keys (e = 65537) from seed 0xBF7C0001.
-Seeded Mersenne-Twister candidates + Miller-Rabin; 31 keys so configs 3 (R=16) and 5 (R=31) can
-give each replica its own key.  Output committed as tests/golden/rsa_keys_bf7c0001.json.
+Seeded Mersenne-Twister candidates + Miller-Rabin; 33 keys so configs 3 (R=16) and 5 (R=31) can
+give each replica its own key (+ 2 for a non-member and an outsider in the n = 31 tests).  Output committed as tests/golden/rsa_keys_bf7c0001.json.
 TEST/BENCH FIXTURE ONLY — these private keys are public."""
 import json, os, random
-SEED, NKEYS = 0xBF7C0001, 31
+SEED, NKEYS = 0xBF7C0001, 33
 rng = random.Random(SEED)
 SMALL = [p for p in range(3, 2000, 2) if all(p % q for q in range(3, int(p ** 0.5) + 1, 2))]
 
