@@ -98,6 +98,8 @@ def load():
         "bftq_graph_set_self": (C.c_int, [vp, C.c_uint64]),
         "bftq_graph_remove_node": (C.c_int, [vp, C.c_uint64]),
         "bftq_graph_revoke": (C.c_int, [vp, C.c_uint64]),
+        "bftq_graph_version": (C.c_int, [vp, u64p, u64p, u64p]),
+        "bftq_equivocation_scan_batch": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, u64p]),
         "bftq_graph_choose_quorum": (C.c_int, [vp, C.c_int, vp, C.c_uint32, u32p, vp, C.c_uint32, u32p]),
         "bftq_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "bftq_measure_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),

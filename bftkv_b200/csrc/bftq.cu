@@ -1533,7 +1533,16 @@ int bftq_pgp_digest_batch(bftq_engine* e, const uint8_t* data_blob, const uint64
 #include "packer_host.inc"
 
 // ---- quorum-descriptor builder ------------------------------------------------------------------
-struct bftq_graph { std::mutex mu; bftq::wot::Graph g; };
+// The descriptor the reference recomputes on EVERY call (client.go:64,101,141,238; server.go:182,211,237,300,473) is a
+// function of the trust graph alone: it is cached per rw flag set and stamped with the graph's version, which every
+// mutation (AddNodes / SetSelfNodes / RemoveNodes / Revoke — certificate revocation included, graph.go:131-146) advances.
+struct bftq_graph {
+  std::mutex mu;
+  bftq::wot::Graph g;
+  uint64_t version = 1;
+  std::map<int, std::pair<uint64_t, std::vector<bftq::wot::QC>>> cache;      // rw -> (version it was built at, cliques)
+  uint64_t hits = 0, builds = 0;
+};
 extern "C" {
 int bftq_graph_create(bftq_graph** out) {
   if (!out) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
@@ -1545,24 +1554,36 @@ int bftq_graph_add_node(bftq_graph* g, uint64_t id, const uint64_t* signer_ids, 
   if (!g || (n_signers && !signer_ids)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::lock_guard<std::mutex> l(g->mu);
   g->g.add_node(id, signer_ids, n_signers);
+  g->version++;
   return BFTQ_OK;
 }
 int bftq_graph_set_self(bftq_graph* g, uint64_t id) {
   if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::lock_guard<std::mutex> l(g->mu);
   g->g.set_self(id);
+  g->version++;
   return BFTQ_OK;
 }
 int bftq_graph_remove_node(bftq_graph* g, uint64_t id) {
   if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::lock_guard<std::mutex> l(g->mu);
   g->g.remove_node(id);
+  g->version++;
   return BFTQ_OK;
 }
 int bftq_graph_revoke(bftq_graph* g, uint64_t id) {
   if (!g) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   std::lock_guard<std::mutex> l(g->mu);
   g->g.revoke(id);
+  g->version++;
+  return BFTQ_OK;
+}
+int bftq_graph_version(bftq_graph* g, uint64_t* version, uint64_t* cache_hits, uint64_t* cache_builds) {
+  if (!g || !version) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> l(g->mu);
+  *version = g->version;
+  if (cache_hits) *cache_hits = g->hits;
+  if (cache_builds) *cache_builds = g->builds;
   return BFTQ_OK;
 }
 int bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint32_t cap_qc, uint32_t* n_qc, uint64_t* out_members,
@@ -1571,7 +1592,13 @@ int bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint
   std::vector<bftq::wot::QC> qcs;
   {
     std::lock_guard<std::mutex> l(g->mu);
-    g->g.choose_quorum(rw, qcs);
+    auto it = g->cache.find(rw);
+    if (it != g->cache.end() && it->second.first == g->version) { qcs = it->second.second; g->hits++; }
+    else {
+      g->g.choose_quorum(rw, qcs);
+      g->cache[rw] = std::make_pair(g->version, qcs);
+      g->builds++;
+    }
   }
   uint32_t off = 0;
   for (size_t c = 0; c < qcs.size(); c++) {
@@ -1580,6 +1607,46 @@ int bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint
   }
   *n_qc = (uint32_t)qcs.size();
   *n_members = off;
+  return BFTQ_OK;
+}
+
+// Client.revoke's scan (protocol/client.go:304-346), batched: per operation, the signers (Signers(ss) of every good
+// response, in bucket order) that appear under two DIFFERENT values at the same timestamp t > 0.  A signer is remembered
+// under the first value it is seen with (dup_map[id] gets exactly one round) and reported the first time it turns up
+// under another one; t == 0 is skipped ("temp solution", :311-314).  The reference walks Go maps, so the ORDER of the
+// reported ids is unspecified there; here it is responder order.  Host-side bookkeeping on ids (no crypto): a hash join.
+int bftq_equivocation_scan_batch(const uint32_t* op_off, uint64_t n_ops, const uint8_t* status, const uint64_t* ts, const uint32_t* value_id,
+                                 const uint32_t* signer_off, const uint64_t* signer_ids, uint32_t* out_off, uint64_t* out_ids, uint64_t cap_ids,
+                                 uint64_t* n_ids) {
+  if (!op_off || !out_off || !n_ids) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  const uint64_t n_items = n_ops ? op_off[n_ops] : 0;
+  if (n_items && (!status || !ts || !value_id || !signer_off)) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  uint64_t total = 0;
+  std::map<std::pair<uint64_t, uint64_t>, uint32_t> first_value;         // (t, signer) -> value id it was first seen with
+  std::vector<uint64_t> revoked;
+  for (uint64_t i = 0; i < n_ops; i++) {
+    out_off[i] = (uint32_t)total;
+    first_value.clear();
+    revoked.clear();
+    for (uint32_t p = op_off[i]; p < op_off[i + 1]; p++) {
+      if (status[p] != 0 || ts[p] == 0) continue;
+      for (uint32_t k = signer_off[p]; k < signer_off[p + 1]; k++) {
+        const uint64_t id = signer_ids[k];
+        auto key = std::make_pair(ts[p], id);
+        auto it = first_value.find(key);
+        if (it == first_value.end()) { first_value[key] = value_id[p]; continue; }
+        if (it->second == value_id[p]) continue;
+        bool seen = false;
+        for (uint64_t r : revoked) if (r == id) { seen = true; break; }
+        if (seen) continue;
+        revoked.push_back(id);
+        if (out_ids && total < cap_ids) out_ids[total] = id;
+        total++;
+      }
+    }
+  }
+  out_off[n_ops] = (uint32_t)total;
+  *n_ids = total;
   return BFTQ_OK;
 }
 

@@ -473,10 +473,25 @@ int  bftq_graph_add_node(bftq_graph* g, uint64_t id, const uint64_t* signer_ids,
 int  bftq_graph_set_self(bftq_graph* g, uint64_t id);                                                   /* graph.go:77-88 */
 int  bftq_graph_remove_node(bftq_graph* g, uint64_t id);                                                /* graph.go:90-108 */
 int  bftq_graph_revoke(bftq_graph* g, uint64_t id);                                                     /* graph.go:131-140 */
+/* The graph's version (advanced by every mutation above) and the descriptor cache's counters: descriptors are cached
+ * per rw and rebuilt only when the version moved — the reference recomputes them on every call. */
+int  bftq_graph_version(bftq_graph* g, uint64_t* version, uint64_t* cache_hits, uint64_t* cache_builds);
 /* wotqs.ChooseQuorum(rw): writes up to cap_qc cliques and cap_members member ids; *n_qc / *n_members
  * receive the required counts (call with caps 0 to size the buffers). */
 int  bftq_graph_choose_quorum(bftq_graph* g, int rw, bftq_qc_ids_t* out_qcs, uint32_t cap_qc, uint32_t* n_qc,
                               uint64_t* out_members, uint32_t cap_members, uint32_t* n_members);
+
+/* Client.revoke's equivocation scan (protocol/client.go:304-346; server side protocol/server.go:354-373), batched: for
+ * every operation the signers that signed two DIFFERENT values at the same timestamp — "same signer, same t, different
+ * value".  Response p of operation i (op_off as everywhere; status 0 = a good response, others are skipped; t == 0 is
+ * skipped as the reference does) carries value_id[p] and the signers of its collective signature,
+ * signer_ids[signer_off[p] .. signer_off[p+1]) (= CollectiveSignature.Signers(ss): bftq_signature_signers).  The ids to
+ * revoke for operation i go to out_ids[out_off[i] .. out_off[i+1]), each once, in responder order (the reference's order
+ * follows Go map iteration and is unspecified); *n_ids = total (call with cap_ids 0 to size out_ids).  Host-side
+ * bookkeeping on ids — no crypto — so it needs no engine. */
+int bftq_equivocation_scan_batch(const uint32_t* op_off, uint64_t n_ops, const uint8_t* status, const uint64_t* ts, const uint32_t* value_id,
+                                 const uint32_t* signer_off, const uint64_t* signer_ids, uint32_t* out_off, uint64_t* out_ids, uint64_t cap_ids,
+                                 uint64_t* n_ids);
 
 /* ---- statistics ------------------------------------------------------------------------------
  * Counters since bftq_init (SURVEY §5 "metrics"): items verified, kernel launches. */

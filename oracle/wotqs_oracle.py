@@ -337,3 +337,30 @@ def read_decide(responses, q: Quorum):
             if q.reject(failure):
                 return READ_REJECTED, k + 1, None, 0
     return READ_EXHAUSTED, len(responses), None, 0
+
+
+def revoke_scan(m: dict, signers_of):
+    """Client.revoke's scan, protocol/client.go:304-346.  m: {t: {value: [signedValue, ...]}} (insertion order =
+    one of Go's legal map orders); signers_of(signedValue) -> [signer id, ...] (CollectiveSignature.Signers(ss)).
+    Returns the ids the reference would revoke, in discovery order: a signer is remembered under the first value
+    bucket ("round") it is seen in — dup_map[id] only ever holds that one round — and revoked the first time it
+    shows up in another bucket of the same t; t == 0 is skipped."""
+    revoked = []
+    for t, vl in m.items():
+        if t == 0:
+            continue
+        dup_map = {}
+        rnd = 0
+        for _, l in vl.items():
+            for sv in l:
+                for sid in signers_of(sv):
+                    if sid in dup_map:
+                        for it in dup_map[sid]:
+                            if it != rnd:
+                                if sid in revoked:
+                                    break
+                                revoked.append(sid)
+                    else:
+                        dup_map[sid] = [rnd]
+            rnd += 1
+    return revoked
