@@ -24,8 +24,11 @@ ErrDecryptionFailed = "crypto: decryption failed"
 ErrInvalidTransportSecurityData = "crypto: invalid transport security data"
 ErrMessageBody = "message body / nonce error"
 ErrMessageUnsupported = "unsupported message form (compressed data)"
+ErrNotBuilt = "gpu: key size / curve not built into libbftq (the shim re-runs the item on crypto/pgp)"
 _ERR = {0: None, -6: ErrInvalidSignature, -7: ErrInsufficientNumberOfSignatures, -8: ErrDecryptionFailed, -9: ErrInvalidTransportSecurityData,
         -10: ErrMessageBody, -11: ErrMessageUnsupported}
+_ERR_SIG = dict(_ERR)
+_ERR_SIG[-11] = ErrNotBuilt
 
 
 def _blob(items: Sequence[bytes]):
@@ -141,7 +144,7 @@ class Signature:
         else:
             cb, co = _blob(certs)
             _lib.check(self._lib.bftq_signature_verify_with_cert_batch(self.keyring._h, p(tb), p(to), p(sb), p(so), p(cb), p(co), n, p(err)))
-        return [_ERR[int(e)] for e in err[:n]]
+        return [_ERR_SIG[int(e)] for e in err[:n]]
 
     def verify(self, tbs: bytes, sig_data: bytes) -> Optional[str]:
         return self.verify_batch([tbs], [sig_data])[0]
@@ -215,7 +218,7 @@ class CollectiveSignature:
         p = lambda a: C.c_void_p(a.ctypes.data)
         _lib.check(self._lib.bftq_collective_verify_batch(self.signature.keyring._h, C.cast(arr, C.c_void_p), len(q.qcs), p(members), nm,
                                                           p(tb), p(to), p(sb), p(so), n, p(err)))
-        return [_ERR[int(e)] for e in err[:n]]
+        return [_ERR_SIG[int(e)] for e in err[:n]]
 
     def verify(self, tbs: bytes, ss_data: bytes, q: Quorum):
         """Returns (error, completed) — the reference sets ss.Completed = true on success."""

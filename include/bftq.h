@@ -57,6 +57,9 @@ extern "C" {
 #define BFTQ_ST_UNKNOWN_SIGNER  4   /* key index out of range / issuer not in keyring            */
 #define BFTQ_ST_UNSUPPORTED     5   /* algorithm the reference's library cannot verify either    */
 #define BFTQ_ST_MISSING         6   /* no response from this replica (tally input only)          */
+#define BFTQ_ST_NOT_BUILT       9   /* a key size / curve / DSA domain the reference's library verifies and this build does not
+                                       (RSA > 4096 bit, DSA p other than 1024 / 2048 bit or q > 256 bit, ECDSA P-384 / P-521): the item is
+                                       reported as BFTQ_ERR_UNSUPPORTED and the shim re-runs it on crypto/pgp                         */
 #define BFTQ_ST_NONCE_MISMATCH  7   /* transport.ErrTransportNonceMismatch (transport.go:121-124)  */
 #define BFTQ_ST_UNVERIFIED_SIGNER 8 /* ACCEPTED, as the reference accepts it: the message's signer is not in the keyring, so
                                        openpgp.ReadMessage leaves SignedBy nil and never checks the signature (read path only) */
@@ -347,7 +350,10 @@ int  bftq_keyring_ids(bftq_keyring* kr, uint64_t* out_ids, uint32_t cap, uint32_
 int  bftq_keyring_certifiers(bftq_keyring* kr, uint64_t key_id, uint64_t* out_ids, uint32_t cap, uint32_t* n);
 
 /* PGPSignature.Verify (crypto_pgp.go:319-330), batched over n_items independent (tbs, sig.Data)
- * pairs: out_err[i] = 0 (nil) or BFTQ_ERR_INVALID_SIGNATURE.  Every signature packet of the
+ * pairs: out_err[i] = 0 (nil), BFTQ_ERR_INVALID_SIGNATURE, or BFTQ_ERR_UNSUPPORTED when the item fails while one of its
+ * packets uses an algorithm / key size the reference's library verifies and this build does not (RSA > 4096 bit,
+ * DSA beyond 1024/2048-bit p or 256-bit q, ECDSA P-384 / P-521, RIPEMD-160): the shim re-runs exactly those items on
+ * crypto/pgp (bftq_stats counts them in unsupported_items).  Every signature packet of the
  * stream must verify, empty data is invalid, unknown issuers are skipped unless they end the
  * stream — exactly the reference's loop over openpgp.CheckDetachedSignature. */
 int bftq_signature_verify_batch(bftq_keyring* kr, const uint8_t* tbs_blob, const uint64_t* tbs_off,
@@ -423,8 +429,9 @@ typedef struct {
 } bftq_qc_ids_t;
 /* PGPCollectiveSignature.Verify (crypto_pgp.go:485-500), batched: valid packets append their
  * signer (no dedupe), invalid / unknown ones are ignored, success as soon as q.IsSufficient
- * (monotone, so the decision equals IsSufficient over all valid signers).  out_err[i] = 0 or
- * BFTQ_ERR_INSUFFICIENT_SIGS; on success the shim sets ss.Completed = true (:494).  The tally runs
+ * (monotone, so the decision equals IsSufficient over all valid signers).  out_err[i] = 0,
+ * BFTQ_ERR_INSUFFICIENT_SIGS, or BFTQ_ERR_UNSUPPORTED (insufficient while a packet could not be judged here, see
+ * bftq_signature_verify_batch); on success the shim sets ss.Completed = true (:494).  The tally runs
  * on the GPU (K2) over the verified signers. */
 int bftq_collective_verify_batch(bftq_keyring* kr, const bftq_qc_ids_t* qcs, uint32_t n_qc, const uint64_t* member_ids,
                                  uint32_t n_members, const uint8_t* tbs_blob, const uint64_t* tbs_off,
@@ -509,8 +516,8 @@ typedef struct {
   uint32_t numa_cpus;        /* CPUs the library's worker threads are bound to (0 = not bound)         */
   uint64_t msg_gpu_items;    /* transport answers parsed + hashed on the GPU (K0m) by bftq_read_responses_batch   */
   uint64_t msg_host_items;   /* ... and the ones K0m flagged, decided through the host packer                    */
-  uint64_t unsupported_items;/* tuples answered BFTQ_ST_UNSUPPORTED by the packer: algorithms / key sizes the
-                                reference's library can verify and this build cannot (INTEGRATION.md "fallback") */
+  uint64_t unsupported_items;/* tuples answered BFTQ_ST_NOT_BUILT by the packer: key sizes / curves the reference's
+                                library can verify and this build cannot (INTEGRATION.md "fallback")              */
 } bftq_stats_t;
 int bftq_stats(bftq_engine* e, bftq_stats_t* out);
 

@@ -180,7 +180,10 @@ func (s *signature) Verify(tbs []byte, sig *bpacket.SignaturePacket) error {
 	if sig == nil {
 		return crypto.ErrInvalidSignature
 	}
-	return s.g.agg.verify(tbs, sig.Data, nil, false)
+	if err := s.g.agg.verify(tbs, sig.Data, nil, false); err != ErrUnsupported {
+		return err
+	}
+	return s.Signature.Verify(tbs, sig) // foreign key kinds (P-384, DSA-3072, RSA > 4096): the reference's own path
 }
 
 func (s *signature) VerifyWithCertificate(tbs []byte, sig *bpacket.SignaturePacket, cert node.Node) error {
@@ -191,7 +194,10 @@ func (s *signature) VerifyWithCertificate(tbs []byte, sig *bpacket.SignaturePack
 	if err != nil {
 		return crypto.ErrInvalidSignature
 	}
-	return s.g.agg.verify(tbs, sig.Data, c, true) // an EMPTY certificate must fail, not fall back to the shared keyring
+	if err := s.g.agg.verify(tbs, sig.Data, c, true); err != ErrUnsupported { // an EMPTY certificate must fail, not fall back to the shared keyring
+		return err
+	}
+	return s.Signature.VerifyWithCertificate(tbs, sig, cert)
 }
 
 // ---- CollectiveSignature (crypto/crypto.go:66-71) ------------------------------------------------------------------
@@ -236,6 +242,9 @@ func (cs *collective) Verify(tbs []byte, ss *bpacket.SignaturePacket, q quorum.Q
 		tb.data.u8(), tb.offs(), sb.data.u8(), sb.offs(), 1, &rc)
 	tb.free()
 	sb.free()
+	if r == 0 && rc == C.BFTQ_ERR_UNSUPPORTED {
+		return cs.CollectiveSignature.Verify(tbs, ss, q) // a packet libbftq could not judge might have tipped the balance
+	}
 	if r != 0 || rc != 0 {
 		return crypto.ErrInsufficientNumberOfSignatures
 	}
@@ -363,10 +372,13 @@ func (a *aggregator) flush(batch []*job) {
 				C.uint64_t(len(sel)), &errs[0])
 		}
 		for i, j := range sel {
-			if rc != 0 || errs[i] != 0 {
-				j.done <- crypto.ErrInvalidSignature // every failure kind collapses to this sentinel (crypto_pgp.go:325-327)
-			} else {
+			switch {
+			case rc == 0 && errs[i] == 0:
 				j.done <- nil
+			case rc == 0 && errs[i] == C.BFTQ_ERR_UNSUPPORTED:
+				j.done <- ErrUnsupported // an algorithm / key size libbftq lacks: the caller below re-runs it on crypto/pgp
+			default:
+				j.done <- crypto.ErrInvalidSignature // every failure kind collapses to this sentinel (crypto_pgp.go:325-327)
 			}
 		}
 	}

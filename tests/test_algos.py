@@ -220,9 +220,10 @@ def test_dsa_flat_api_random_domain(engine):
 def test_packer_mixed_algorithms(engine, algos, ring, golden):
     """One keyring holding RSA, ECDSA and DSA keys; Signature.Verify over the GnuPG fixtures of all three.
     DSA-3072 is outside K5's modulus classes: the packer must say UNSUPPORTED (an error), never 'valid'."""
-    from bftkv_b200.crypto_gpu import Keyring, Signature
+    from bftkv_b200.crypto_gpu import ErrNotBuilt, Keyring, Signature
     kr = Keyring(engine)
     ents = list(ring)
+    u0 = engine.stats()["unsupported_items"]
     for k in algos["keys"].values():
         assert kr.register(bytes.fromhex(k["pub"])) == 1
     for n in ("a01", "a02"):
@@ -241,11 +242,12 @@ def test_packer_mixed_algorithms(engine, algos, ring, golden):
     sig += [bytes.fromhex(by[t0]["p256a"] + by[t0]["dsa2048"]), bytes.fromhex(by[t0]["dsa1024"] + by[t0]["p256b"])]
     got = Signature(kr).verify_batch(tbs, sig)
     ref = [pgp.signature_verify(ents, t, s) for t, s in zip(tbs, sig)]
-    big = {i for i, c in enumerate(cases) if c["signer"] == "dsa3072"}
+    big = {i + k for i, c in enumerate(cases) if c["signer"] == "dsa3072" for k in (0, len(cases))}       # genuine and tampered copies alike
     for i, (a, b) in enumerate(zip(got, ref)):
         if i in big:
-            assert a is not None                       # documented gap: 3072-bit DSA domain is not built
+            assert a == ErrNotBuilt                    # 3072-bit DSA domain is not built: reported as such (BFTQ_ERR_UNSUPPORTED), the shim re-runs it on crypto/pgp
         else:
             assert a == b, (i, a, b)
     assert sum(r is None for r in ref) == len(cases) + 2
+    assert engine.stats()["unsupported_items"] - u0 == len(big) > 0        # counted for the operator (bftq_stats)
     kr.close()
