@@ -40,6 +40,7 @@ def load():
         "bftq_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "bftq_shutdown": (None, [vp]),
         "bftq_device_sm_count": (C.c_int, [vp]),
+        "bftq_engine_set_verify_flags": (C.c_int, [vp, C.c_uint32]),
         "bftq_host_alloc": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
         "bftq_host_free": (C.c_int, [vp, vp]),
         "bftq_bind_thread": (C.c_int, [vp]),

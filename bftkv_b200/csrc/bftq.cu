@@ -202,6 +202,7 @@ struct bftq_engine {
   bool numa_valid = false;
   cpu_set_t numa_cpus;
   std::map<void*, size_t> host_allocs;           // bftq_host_alloc blocks
+  uint32_t packer_flags = 0;   // BFTQ_F_* the packet-level entry points pass to K1 (bftq_engine_set_verify_flags / env BFTQ_STRICT_RANGE)
   int rsa_t = 4;          // lanes per signature (env BFTQ_RSA_T)
   int rsa_block = 128;
 };
@@ -554,6 +555,7 @@ int bftq_init(int device, bftq_engine** out) {
     int v = atoi(t);
     if (v == 4 || v == 8) e->rsa_t = v;
   }
+  if (const char* v = getenv("BFTQ_STRICT_RANGE")) if (atoi(v) > 0) e->packer_flags |= BFTQ_F_STRICT_RANGE;
   numa_probe(e);
   e->pool.on_start = [e] { numa_bind_this_thread(e); };
   *out = e;
@@ -611,6 +613,12 @@ void bftq_shutdown(bftq_engine* e) {
 }
 
 int bftq_device_sm_count(bftq_engine* e) { return e ? e->sm_count : BFTQ_ERR_INVALID_ARG; }
+int bftq_engine_set_verify_flags(bftq_engine* e, uint32_t flags) {
+  if (!e || (flags & ~(uint32_t)BFTQ_F_STRICT_RANGE)) return fail(BFTQ_ERR_INVALID_ARG, "unknown flag");
+  std::lock_guard<std::mutex> g(e->mu);
+  e->packer_flags = flags;
+  return BFTQ_OK;
+}
 int bftq_key_count(bftq_engine* e) {
   if (!e) return BFTQ_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(e->mu);

@@ -74,17 +74,20 @@ msg_parse_digest_kernel(const uint8_t* __restrict__ msg_blob, const uint64_t* __
                         uint8_t* __restrict__ out_pre, uint8_t* __restrict__ out_where, uint8_t* __restrict__ out_aux, uint64_t* __restrict__ out_ts,
                         uint32_t* __restrict__ out_voff, uint32_t* __restrict__ out_vlen, uint32_t* __restrict__ out_plen,
                         uint64_t* __restrict__ out_signed_by) {
+  // the SHA-256 message block of every thread lives in shared memory (word-major: conflict-free), so the byte stream can be
+  // absorbed with a dynamic word index without spilling sixteen registers to local memory
+  __shared__ uint32_t w_s[16][128];
   const uint32_t item_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = item_raw < n_items;
   const uint32_t item = live ? item_raw : n_items - 1;
   const int lane = threadIdx.x & 31;
   const uint64_t o0 = msg_off[item] - msg_base, o1 = msg_off[item + 1] - msg_base;
   const uint8_t* m = msg_blob + o0;
-  uint8_t* plain = plain_blob + o0;
+  uint8_t* plain = plain_blob + ((o0 + 3) & ~(uint64_t)3);        // 4-byte aligned inside the item's span (the fast path stores words)
   uint8_t where = kParseDecided, pre = 0, aux = 0;
   uint32_t kidx = 0, plen = 0, voff = 0, vlen = 0;
   uint64_t ts = 0, signed_by = 0;
-  bool copy = false, hash = false;
+  bool copy = false;
   fastparse::FastSig f;
   f.mpi_off = 0; f.mpi_len = 0; f.hashed_off = 0; f.hashed_len = 0; f.tag = 0;
   uint32_t sig_at = 0;
@@ -114,80 +117,142 @@ msg_parse_digest_kernel(const uint8_t* __restrict__ msg_blob, const uint64_t* __
       if (okh) { name_len = b; if (name_len > (uint32_t)kMaxFastName) okh = false; }
       for (uint32_t i = 0; okh && i < name_len; i++) { okh = r.get(b); name[i] = b; }
       for (int i = 0; okh && i < 4; i++) okh = r.get(b);
-      // ---- body: de-chunk into the scratch
-      if (okh) { while (r.get(b)) plain[plen++] = b; }
       if (!okh || r.bad) where = kParseHost;
       else {
-        sig_at = r.pos;
-        // ---- exactly one v4 RSA / SHA-256 signature packet to the end of the message
-        if (sig_at >= n || fastparse::parse(m + sig_at, (size_t)(n - sig_at), f) != fastparse::kFast || f.hash_id != 8) where = kParseHost;
-        else {
-          // md.SignedBy = first key of KeysByIdUsage(one-pass key id, sign): unknown -> SignatureError stays nil
-          int hit = -1;
-          for (uint32_t i = 0; i < n_issuers; i++) if (issuers[i].key_id == signed_by) { hit = (int)i; break; }
-          if (hit < 0) pre = kStUnverifiedSigner;
-          else {
-            const IssuerEntry en = issuers[hit];
-            if (en.kind != 0) where = kParseHost;
-            else {
-              kidx = en.key_idx;
-              hash = true;
-              if (en.algo != f.pk_algo) pre = 1;
-              if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }
-              else copy = true;
+        // ---- ONE loop over the hashed byte stream: the literal body (de-chunked into the scratch as it passes), then — once the
+        // signature packet behind it has been parsed and its signer found — the packet's hashed area, the v4 trailer and the
+        // SHA-256 padding.  A single absorb / compress site keeps the kernel small.
+        uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        uint32_t cur = 0, tot = 0, spos = 0, msg_bytes = 0;
+        int phase = 0, pad_state = 0, pad_k = 0;                 // 0 body, 1 suffix, 2 padding
+        const uint8_t* suf = nullptr;
+        bool done = false, hashing = true;
+        while (!done) {
+          // ---- fast path: a whole 64-byte block of the body inside one chunk, at a block boundary of the hash — seventeen
+          // independent aligned word loads (latency overlapped), funnel-shifted to the stream's alignment, one compress, sixteen
+          // word stores into the scratch.  Everything else (chunk headers, the tail, the suffix, the padding) takes the byte loop.
+          while (phase == 0 && (tot & 63u) == 0u && r.rem >= 64u) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(m + r.pos);
+            const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            uint32_t x[17];
+#pragma unroll
+            for (int i = 0; i < 17; i++) x[i] = __ldg(aw + i);        // x[16] may lie up to 3 bytes behind the message: inside the buffer's slack
+            uint32_t w[16];
+            uint32_t* pw = reinterpret_cast<uint32_t*>(plain + plen);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const uint32_t le = __funnelshift_r(x[i], x[i + 1], sh);
+              pw[i] = le;
+              w[i] = __byte_perm(le, 0, 0x0123);
             }
+            sha256_compress(h, w);
+            r.pos += 64u; r.rem -= 64u; tot += 64u; plen += 64u;
           }
-          if (where == kParseDecided) {
-            // ---- nonce: base64.StdEncoding.DecodeString(FileName) == the request's nonce (CR / LF skipped, padding mandatory)
-            uint8_t dec[kMaxNonce]; uint32_t nd = 0; uint8_t q[4]; int nq = 0; bool closed = false, corrupt = false;
-            for (uint32_t i = 0; i < name_len && !corrupt; i++) {
-              const uint8_t c = name[i];
-              if (c == '\r' || c == '\n') continue;
-              if (closed) { corrupt = true; break; }
-              if (c == '=') {
-                if (nq < 2) { corrupt = true; break; }
-                if (nq == 2) {
-                  uint32_t j = i + 1;
-                  while (j < name_len && (name[j] == '\r' || name[j] == '\n')) j++;
-                  if (j >= name_len || name[j] != '=') { corrupt = true; break; }
-                  i = j;
+          if (phase == 0) {
+            if (r.get(b)) plain[plen++] = b;
+            else {
+              // ---- the body has ended: everything that decides whether (and against which key) the digest is needed
+              hashing = false;
+              if (r.bad) { where = kParseHost; break; }
+              sig_at = r.pos;
+              if (sig_at >= n || fastparse::parse(m + sig_at, (size_t)(n - sig_at), f) != fastparse::kFast || f.hash_id != 8) { where = kParseHost; break; }
+              int hit = -1;                                      // md.SignedBy = first key of KeysByIdUsage(one-pass key id, sign)
+              for (uint32_t i = 0; i < n_issuers; i++) if (issuers[i].key_id == signed_by) { hit = (int)i; break; }
+              if (hit < 0) pre = kStUnverifiedSigner;            // unknown signer: SignatureError stays nil, nothing is verified
+              else {
+                const IssuerEntry en = issuers[hit];
+                if (en.kind != 0) { where = kParseHost; break; }
+                kidx = en.key_idx;
+                hashing = true;
+                if (en.algo != f.pk_algo) pre = 1;
+                if (f.mpi_len > en.kbytes) { if (!pre) pre = 1; }
+                else copy = true;
+              }
+              // ---- nonce: base64.StdEncoding.DecodeString(FileName) == the request's nonce (CR / LF skipped, padding mandatory)
+              {
+                uint8_t dec[kMaxNonce]; uint32_t nd = 0; uint8_t q[4] = {0, 0, 0, 0}; int nq = 0; bool closed = false, corrupt = false;
+                for (uint32_t i = 0; i < name_len && !corrupt; i++) {
+                  const uint8_t c = name[i];
+                  if (c == '\r' || c == '\n') continue;
+                  if (closed) { corrupt = true; break; }
+                  if (c == '=') {
+                    if (nq < 2) { corrupt = true; break; }
+                    if (nq == 2) {
+                      uint32_t j = i + 1;
+                      while (j < name_len && (name[j] == '\r' || name[j] == '\n')) j++;
+                      if (j >= name_len || name[j] != '=') { corrupt = true; break; }
+                      i = j;
+                    }
+                    const int v0 = b64val(q[0]), v1 = b64val(q[1]), v2 = nq > 2 ? b64val(q[2]) : 0;
+                    if (nd + 2 > (uint32_t)kMaxNonce) { corrupt = true; break; }
+                    dec[nd++] = (uint8_t)((v0 << 2) | (v1 >> 4));
+                    if (nq > 2) dec[nd++] = (uint8_t)(((v1 & 15) << 4) | (v2 >> 2));
+                    nq = 0; closed = true;
+                    continue;
+                  }
+                  if (b64val(c) < 0) { corrupt = true; break; }
+                  q[nq++] = c;
+                  if (nq == 4) {
+                    if (nd + 3 > (uint32_t)kMaxNonce) { corrupt = true; break; }
+                    const int v0 = b64val(q[0]), v1 = b64val(q[1]), v2 = b64val(q[2]), v3 = b64val(q[3]);
+                    dec[nd++] = (uint8_t)((v0 << 2) | (v1 >> 4)); dec[nd++] = (uint8_t)(((v1 & 15) << 4) | (v2 >> 2)); dec[nd++] = (uint8_t)(((v2 & 3) << 6) | v3);
+                    nq = 0;
+                  }
                 }
-                const int v0 = b64val(q[0]), v1 = b64val(q[1]), v2 = nq > 2 ? b64val(q[2]) : 0;
-                if (nd + 2 > (uint32_t)kMaxNonce) { corrupt = true; break; }
-                dec[nd++] = (uint8_t)((v0 << 2) | (v1 >> 4));
-                if (nq > 2) dec[nd++] = (uint8_t)(((v1 & 15) << 4) | (v2 >> 2));
-                nq = 0; closed = true;
-                continue;
+                if (nq != 0) corrupt = true;
+                if (corrupt) aux |= kAuxNonceCorrupt;              // Decrypt returns the base64 error BEFORE looking at SignatureError
+                else {
+                  bool same = nd == nonce_len;
+                  for (uint32_t i = 0; same && i < nonce_len; i++) same = dec[i] == nonce_blob[(size_t)item * nonce_len + i];
+                  if (!same) aux |= kAuxNonceMismatch;
+                }
               }
-              if (b64val(c) < 0) { corrupt = true; break; }
-              q[nq++] = c;
-              if (nq == 4) {
-                if (nd + 3 > (uint32_t)kMaxNonce) { corrupt = true; break; }
-                const int v0 = b64val(q[0]), v1 = b64val(q[1]), v2 = b64val(q[2]), v3 = b64val(q[3]);
-                dec[nd++] = (uint8_t)((v0 << 2) | (v1 >> 4)); dec[nd++] = (uint8_t)(((v1 & 15) << 4) | (v2 >> 2)); dec[nd++] = (uint8_t)(((v2 & 3) << 6) | v3);
-                nq = 0;
+              // ---- processResponse: packet.Parse of a non-empty answer
+              if (plen > 0) {
+                const pkt::View v = pkt::parse(plain, plen);
+                if (v.err) aux |= kAuxPacketError;
+                else { ts = v.t; voff = v.value_off; vlen = v.value_len; }
               }
+              if (!hashing || (pre != 0 && pre != 1)) { hashing = false; break; }
+              suf = m + sig_at + f.hashed_off;
+              phase = 1;
+              continue;
             }
-            if (nq != 0) corrupt = true;
-            if (corrupt) aux |= kAuxNonceCorrupt;                  // Decrypt returns the base64 error BEFORE looking at SignatureError
-            else {
-              bool same = nd == nonce_len;
-              for (uint32_t i = 0; same && i < nonce_len; i++) same = dec[i] == nonce_blob[(size_t)item * nonce_len + i];
-              if (!same) aux |= kAuxNonceMismatch;
-            }
-            // ---- processResponse: packet.Parse of a non-empty answer
-            if (plen > 0) {
-              const pkt::View v = pkt::parse(plain, plen);
-              if (v.err) aux |= kAuxPacketError;
-              else { ts = v.t; voff = v.value_off; vlen = v.value_len; }
+          } else if (phase == 1) {
+            const uint32_t hl = f.hashed_len;
+            if (spos < hl) b = suf[spos];
+            else if (spos < hl + 6) { const uint32_t q = spos - hl; b = q == 0 ? 0x04 : q == 1 ? 0xff : (uint8_t)((hl >> (8 * (5 - q))) & 0xffu); }
+            else { phase = 2; msg_bytes = tot; continue; }
+            spos++;
+          } else {
+            if (pad_state == 0) { b = 0x80; pad_state = 1; }
+            else if (pad_state == 1) { if ((tot & 63u) != 56u) b = 0; else { pad_state = 2; continue; } }
+            else { const uint64_t bits = (uint64_t)msg_bytes * 8ull; b = (uint8_t)(bits >> (8 * (7 - pad_k))); pad_k++; if (pad_k == 8) done = true; }
+          }
+          // ---- absorb one byte; every fourth completes a word, every 64th a block
+          cur = (cur << 8) | b;
+          tot++;
+          if ((tot & 3u) == 0u) {
+            w_s[((tot - 1u) >> 2) & 15u][threadIdx.x] = cur;
+            if ((tot & 63u) == 0u) {
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; i++) w[i] = w_s[i][threadIdx.x];
+              sha256_compress(h, w);
             }
           }
+        }
+        if (where == kParseDecided && hashing) {
+          uint32_t* o = reinterpret_cast<uint32_t*>(out_digest + (size_t)item * 32);
+#pragma unroll
+          for (int i = 0; i < 8; i++) o[i] = __byte_perm(h[i], 0, 0x0123);
+          if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;     // BFTQ_ST_HASH_TAG
         }
       }
     }
   }
-  if (where == kParseHost) { pre = 6; hash = false; copy = false; }       // K1 leaves the item alone; the host packer decides it
-  if (pre != 0 && pre != 1) { hash = false; }
+  if (where == kParseHost) { pre = 6; copy = false; aux = 0; }    // K1 leaves the item alone; the host packer decides it
   if (!live) copy = false;
   // ---- per warp: left-pad the signature MPIs into K1's layout, coalesced (as K0)
   const uint64_t src_pos = o0 + sig_at + f.mpi_off;
@@ -211,29 +276,6 @@ msg_parse_digest_kernel(const uint8_t* __restrict__ msg_blob, const uint64_t* __
       }
       dst[t * 32 + lane] = v;
     }
-  }
-  // ---- digest: SHA-256(body || hashed area || 04 FF len32) + the 16-bit quick check
-  if (hash && live) {
-    FastSrc src{plain, m + sig_at + f.hashed_off, plen, f.hashed_len, 0};
-    src.total = src.dlen + src.hlen + 6;
-    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-    const uint32_t nblocks = (src.total + 9 + 63) / 64;
-    for (uint32_t blk = 0; blk < nblocks; blk++) {
-      uint32_t w[16];
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) v = (v << 8) | src.byte(blk * 64 + 4 * i + b);
-        w[i] = v;
-      }
-      if (blk == nblocks - 1) { w[14] = 0u; w[15] = src.total * 8u; }
-      sha256_compress(h, w);
-    }
-    uint32_t* o = reinterpret_cast<uint32_t*>(out_digest + (size_t)item * 32);
-#pragma unroll
-    for (int i = 0; i < 8; i++) o[i] = __byte_perm(h[i], 0, 0x0123);
-    if (!pre && (uint16_t)(h[0] >> 16) != f.tag) pre = 2;
   }
   if (live) {
     out_key_idx[item] = kidx; out_pre[item] = pre; out_where[item] = where; out_aux[item] = aux;

@@ -262,14 +262,20 @@ def sig_packet_v3(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_typ
     return _old_packet(2, body)
 
 
-def sig_packet_v4(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_type: int = 0) -> bytes:
-    """A version-4 RSA signature packet with any digest (hashed: creation time; unhashed: issuer)."""
+def sig_packet_v4(k, key_id: int, hash_id: int, data: bytes, ctime: int, sig_type: int = 0, plus_n: bool = False) -> bytes:
+    """A version-4 RSA signature packet with any digest (hashed: creation time; unhashed: issuer).
+    plus_n: store s + n instead of s (same residue; Go 1.13 accepts it, Go >= 1.20 rejects s >= n) — None if s + n needs 2049 bits."""
     signed = canonical_text(data) if sig_type == 1 else data
     hashed = bytes([5, 2]) + struct.pack(">I", ctime)
     head = bytes([4, sig_type, 1, hash_id]) + struct.pack(">H", len(hashed)) + hashed
     d = hashlib.new(_HASHLIB[hash_id], signed + head + b"\x04\xff" + struct.pack(">I", len(head))).digest()
     unhashed = bytes([9, 16]) + struct.pack(">Q", key_id)
-    return _old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + d[:2] + _mpi(raw_rsa_sign(k, hash_id, d)))
+    sv = raw_rsa_sign(k, hash_id, d)
+    if plus_n:
+        sv += k["n"]
+        if sv.bit_length() > 2048:
+            return None
+    return _old_packet(2, head + struct.pack(">H", len(unhashed)) + unhashed + d[:2] + _mpi(sv))
 
 
 # ---- transport messages: what openpgp.Encrypt(signer) puts inside the SymmetricallyEncrypted packet --------------------

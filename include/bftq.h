@@ -99,6 +99,11 @@ int  bftq_host_free(bftq_engine* e, void* p);
 int  bftq_bind_thread(bftq_engine* e);
 int  bftq_version(void);
 int  bftq_device_sm_count(bftq_engine* e);
+/* BFTQ_F_* flags the packet-level entry points (Signature / CollectiveSignature / Message / read path) pass to K1.  Default 0
+ * = Go 1.13 (the version go.mod pins): rsa.VerifyPKCS1v15 computes s^e mod n for any k-byte s.  A deployment built with
+ * Go >= 1.20 (the reference's Dockerfile is `FROM golang`) rejects s >= n: set BFTQ_F_STRICT_RANGE (or env
+ * BFTQ_STRICT_RANGE=1 at bftq_init). */
+int  bftq_engine_set_verify_flags(bftq_engine* e, uint32_t flags);
 
 /* ---- key table ------------------------------------------------------------------------------
  * Replaces the keyring lookup inside openpgp.CheckDetachedSignature (EntityList.KeysByIdUsage),

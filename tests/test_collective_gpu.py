@@ -98,3 +98,28 @@ def test_collective_verify_matches_oracle(world, n, params, gpu_parse):
     ref = [pgp.collective_verify(w["ents"], t, s, oq)[0] for t, s in zip(tbs_list, streams)]
     assert got == ref
     assert 40 < sum(r is None for r in ref) < 220, sum(r is None for r in ref)
+
+
+def test_strict_range_policy_through_the_packer(world):
+    """s + n has the same residue as s: Go 1.13's rsa.VerifyPKCS1v15 (the version go.mod pins) accepts it, Go >= 1.20 rejects
+    s >= n.  The packet-level entry points follow the engine's policy flag (bftq_engine_set_verify_flags)."""
+    import ctypes as C
+    from bftkv_b200 import _lib
+    w = world
+    sig_api = Signature(w["kr"])
+    tbs = w["tbs"][0]
+    items = []
+    for i in range(NK - 1):
+        p = workload.sig_packet_v4(w["keys"][i], w["kids"][i], 8, tbs, 0x5F000000 + i, plus_n=True)
+        if p is not None:
+            items.append(p)
+    assert len(items) >= 4                                   # s + n < 2^2048 for a good part of the keys
+    plain = [w["sigs"][(0, 0)]] * 2
+    lib, h = w["engine"]._lib, w["engine"]._h
+    try:
+        assert sig_api.verify_batch([tbs] * (len(items) + 2), items + plain) == [None] * (len(items) + 2)
+        _lib.check(lib.bftq_engine_set_verify_flags(h, 1))   # BFTQ_F_STRICT_RANGE
+        got = sig_api.verify_batch([tbs] * (len(items) + 2), items + plain)
+        assert got == ["crypto: invalid signature"] * len(items) + [None] * 2
+    finally:
+        _lib.check(lib.bftq_engine_set_verify_flags(h, 0))
