@@ -476,14 +476,19 @@ int launch_rsa_any(bftq_engine* e, const KeyView& kv, const uint32_t* d_key_idx,
     static const int min_blocks = [] { const char* v = getenv("BFTQ_R32_BLOCKS"); return v ? atoi(v) : 4; }();
     using kern_t = void (*)(const bftq::r32::RsaKey32*, uint32_t, const uint32_t*, const uint8_t*, const uint8_t*, uint32_t, uint64_t, uint32_t,
                             const uint8_t*, uint8_t*);
-    kern_t kern = sq ? (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, true> : (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 4, true>)
-                     : (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, false> : (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 4, false>);
+#ifndef BFTQ_K1_BLOCK
+#define BFTQ_K1_BLOCK 128
+#endif
+    constexpr int kBlk = BFTQ_K1_BLOCK, kMinB = 512 / BFTQ_K1_BLOCK;      // 16 warps per SM either way
+    kern_t kern = sq ? (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, true> : (kern_t)bftq::r32::rsa_verify_r32_kernel<kBlk, kMinB, true>)
+                     : (min_blocks == 3 ? (kern_t)bftq::r32::rsa_verify_r32_kernel<128, 3, false> : (kern_t)bftq::r32::rsa_verify_r32_kernel<kBlk, kMinB, false>);
+    const int blk = min_blocks == 3 ? 128 : kBlk;
     static thread_local int occ32 = 0;
-    if (!occ32) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, kern, 128, 0)); if (occ32 < 1) occ32 = 1; }
-    const uint64_t per_block = 4 * 8;
+    if (!occ32) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, kern, blk, 0)); if (occ32 < 1) occ32 = 1; }
+    const uint64_t per_block = (uint64_t)(blk / 32) * 8;
     uint64_t grid = std::min<uint64_t>((n_items + per_block - 1) / per_block, (uint64_t)e->sm_count * occ32);
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 128, 0, st>>>(kv.d_keys32, kv.nkeys, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
+    kern<<<(unsigned)grid, blk, 0, st>>>(kv.d_keys32, kv.nkeys, d_key_idx, d_sig, d_digest, hash_alg, n_items, flags,
                                          d_pre, d_status);
     CU(cudaGetLastError());
     return BFTQ_OK;

@@ -105,6 +105,7 @@ __device__ __forceinline__ void sqr_iter(Acc<16>& A, uint32_t& cin, uint32_t& Z,
 }
 
 // out = a * a * R^-1 mod n, out < R ("almost Montgomery"), R = 2^2048.  All 32 lanes of the warp call this together.
+template <bool STEP_SYNC = false>
 __device__ __forceinline__ void mont_sqr(uint32_t (&out)[16], const uint32_t (&a)[16], const uint32_t (&n)[16], const uint32_t n0inv,
                                          const int r, const int gbase) {
   constexpr int W = 16;
@@ -125,6 +126,7 @@ __device__ __forceinline__ void mont_sqr(uint32_t (&out)[16], const uint32_t (&a
   constexpr int kSqrUnroll = BFTQ_SQR_UNROLL;      // owner steps per loop body (code size x this)
 #pragma unroll kSqrUnroll
   for (int owner = 0; owner < T; owner++) {
+    if (STEP_SYNC) __syncthreads();             // keep the block's warps in phase (see BFTQ_K1_SYNC in rsa_verify_r32.cuh)
     sqr_iter<0>(A, cin, Z, a2, n, n0inv, r, gbase, owner);
     sqr_iter<2>(A, cin, Z, a2, n, n0inv, r, gbase, owner);
     sqr_iter<4>(A, cin, Z, a2, n, n0inv, r, gbase, owner);

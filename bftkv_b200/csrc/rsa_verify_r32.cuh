@@ -202,7 +202,7 @@ __device__ __forceinline__ void mont_finish(uint32_t (&out)[W], Acc<W>& A, const
 
 // out = a * b * R^-1 mod n with R = 2^(128 W), out < R ("almost Montgomery").  a, b < R as W limbs/lane.
 // All 32 lanes of the warp must call this together.
-template <int W>
+template <int W, bool STEP_SYNC = false>
 __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)[W], const uint32_t (&b)[W],
                                          const uint32_t (&n)[W], const uint32_t n0inv, const int r, const int gbase) {
   Acc<W> A;
@@ -218,6 +218,7 @@ __device__ __forceinline__ void mont_mul(uint32_t (&out)[W], const uint32_t (&a)
   constexpr int kMulUnroll = BFTQ_MUL_UNROLL;      // owner steps per loop body (code size x this)
 #pragma unroll kMulUnroll
   for (int owner = 0; owner < T; owner++) {
+    if (STEP_SYNC) __syncthreads();             // keep the block's warps in phase (see BFTQ_K1_SYNC)
     const int src = gbase + owner;
 #pragma unroll
     for (int jj = 0; jj < W; jj += 2) {
@@ -311,6 +312,9 @@ struct RsaKey32 {               // per key, radix 2^32 little-endian words
   uint32_t pad;
 };
 
+#ifndef BFTQ_K1_SYNC
+#define BFTQ_K1_SYNC 0
+#endif
 // SQ: the squarings of the exponentiation go through mont_sqr (rsa_square_r32.cuh) instead of mont_mul(y, y).
 template <int BLOCK, int MIN_BLOCKS, bool SQ>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
@@ -323,6 +327,8 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
   // s*R mod n is only needed again for exponents with interior 1 bits (never for 65537): park it in
   // shared memory instead of 16 registers.
   __shared__ uint32_t xm_s[W][BLOCK];
+  __shared__ int nbmax_s;
+  constexpr bool kStepSync = BFTQ_K1_SYNC >= 3;
   const int lane = threadIdx.x & 31;
   const int r = lane & (T - 1);
   const int gbase = lane & ~(T - 1);
@@ -332,7 +338,12 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
   const uint64_t warps_total = (uint64_t)gridDim.x * (BLOCK / 32);
   const uint32_t gmask = ((1u << T) - 1u) << gbase;
 
-  for (uint64_t wbase = warp_global * kGroupsPerWarp; wbase < n_items; wbase += warps_total * kGroupsPerWarp) {
+  // The trip count is uniform over the block (a warp whose eight signatures lie behind the end computes on clamped items
+  // and stores nothing), so the warps of a block may meet at barriers: BFTQ_K1_SYNC 1 = once per task, 2 = after every
+  // Montgomery product.  Warps that stay in phase fetch the same instructions at the same time (the hot loop is 15 KB).
+  for (uint64_t bbase = (uint64_t)blockIdx.x * (BLOCK / 32) * kGroupsPerWarp; bbase < n_items; bbase += warps_total * kGroupsPerWarp) {
+    const uint64_t wbase = bbase + (uint64_t)(threadIdx.x >> 5) * kGroupsPerWarp;
+    if (BFTQ_K1_SYNC >= 1) __syncthreads();
     const uint64_t item_raw = wbase + (uint64_t)(lane / T);
     const bool valid = item_raw < n_items;
     const uint64_t item = valid ? item_raw : (n_items - 1);
@@ -363,10 +374,18 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
     int nbmax = nb;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) nbmax = max(nbmax, __shfl_xor_sync(kFull, nbmax, o));
+    if (BFTQ_K1_SYNC >= 2) {                                 // barriers inside the exponent loop: its trip count must be uniform over the block
+      if (threadIdx.x == 0) nbmax_s = 0;
+      __syncthreads();
+      if (lane == 0) atomicMax(&nbmax_s, nbmax);
+      __syncthreads();
+      nbmax = nbmax_s;
+    }
 #pragma unroll 1
     for (int bit = nbmax - 2; bit >= 1; bit--) {
       const bool active = bit <= nb - 2;
-      if (SQ) mont_sqr(t, y, nd, n0inv, r, gbase); else mont_mul(t, y, y, nd, n0inv, r, gbase);
+      if (SQ) mont_sqr<kStepSync>(t, y, nd, n0inv, r, gbase); else mont_mul<W, kStepSync>(t, y, y, nd, n0inv, r, gbase);
+      if (BFTQ_K1_SYNC >= 2) __syncthreads();
       if (active) {
 #pragma unroll
         for (int j = 0; j < W; j++) y[j] = t[j];
