@@ -44,8 +44,9 @@ ITEMS = 65536
 NKEYS = 16
 WORKLOAD = ("batch 65536 RSA-2048 PGP signature verifies (BASELINE configs[1]), 16 keys, e=65537, SHA-256, "
             "1% corrupted + 0.1% unknown signer")
-ED25519_FIELD_MULS = 120 * 8 + 267   # expected 120 non-zero signed 4-bit digits x 8 fe_mul per cached addition + inversion (265) + 2
-ED25519_MACS = ED25519_FIELD_MULS * 110     # fe_mul: 100 limb products + 10 (19 * g) IMADs
+# K1b (ed25519_fast.cuh): expected 63.75 non-zero signed radix-256 digits x 7 field products (100 IMAD.WIDE each) per mixed addition
+# + 126 word products of the Barrett reduction + kernel 2: 5 products per signature + 1/8 of an inversion (254 squarings x 55 + 11 x 100)
+ED25519_MACS = int(63.75 * 700 + 126 + 500 + (254 * 55 + 11 * 100) / 8)        # = 47 134 executed 32x32->64 multiplies per verification
 
 
 def host_cores():
@@ -565,8 +566,11 @@ def run_gpu(args, rank, local_rank, world):
     q6steps = max(2, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
+    q6_each = []
     for _ in range(q6steps):
+        t1 = time.perf_counter()
         got6 = q6step()
+        q6_each.append((time.perf_counter() - t1) * 1e3)
     q6_s = time.perf_counter() - t0
     barrier()
     s61 = eng6.stats()
@@ -614,7 +618,7 @@ def run_gpu(args, rank, local_rank, world):
         de_st = torch.empty(NE, dtype=torch.uint8, device=dev)
 
         def estep():
-            L_.check(eng._lib.bftq_ed25519_verify_batch_dev(eng._h, C.c_void_p(de[0].data_ptr()), 15, C.c_void_p(de[1].data_ptr()),
+            L_.check(eng._lib.bftq_ed25519_verify_batch_dev(eng._h, pk_arr.ctypes.data_as(C.c_void_p), 15, C.c_void_p(de[1].data_ptr()),
                                                             C.c_void_p(de[2].data_ptr()), C.c_void_p(de[3].data_ptr()), NE,
                                                             C.c_void_p(de_st.data_ptr()), C.c_void_p(stream.cuda_stream)))
         estep()
@@ -749,7 +753,7 @@ def run_gpu(args, rank, local_rank, world):
                                           "decisions_rank0": dec_hist, "checked": "statuses vs expectation on every rank; decisions vs the C oracle on rank 0",
                                           "data": "synthetic; tuples drawn from a pool of %d genuine signatures over 31 keys" % args.pool5}},
                        "e2e_packets": {"metric": "quorum_certified_read_ops_per_sec", "value": M6 * world * q6steps / (q6_ms * 1e-3), "unit": "ops/s",
-                                       "answers_per_sec": N6 * world * q6steps / (q6_ms * 1e-3), "steps": q6steps, "ms_per_step": q6_ms / q6steps,
+                                       "answers_per_sec": N6 * world * q6steps / (q6_ms * 1e-3), "steps": q6steps, "ms_per_step": q6_ms / q6steps, "ms_each_step_rank0": [round(x, 3) for x in q6_each],
                                        "h2d_bytes_per_step": int(q6_info["h2d_bytes_per_step"]), "bytes_per_answer": q6_info["bytes_per_answer"],
                                        "h2d_gbps_achieved": q6_info["h2d_bytes_per_step"] * q6steps / (q6_ms * 1e-3) / 1e9,
                                        "api": "bftq_read_responses_batch: the decrypted transport answers (one-pass signature, partial-length literal data, signature) in "
@@ -785,8 +789,9 @@ def run_gpu(args, rank, local_rank, world):
         out["roofline_secondary"]["k1b_ed25519"] = {
             "bound": "int_alu", "achieved": ED25519_MACS * ed["value"] / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s",
             "frac": ED25519_MACS * ed["value"] / int_peak, "executed_macs_per_verify": ED25519_MACS,
-            "note": "windowed kernel: expected 120 cached additions x 8 fe_mul + 267 for the final inversion/encoding = %d field multiplications x 110 "
-                    "IMAD (10x10 limbs + 10 pre-scalings), one thread per signature; SHA-512 and the scalar reduction not counted" % ED25519_FIELD_MULS}
+            "note": "cached radix-256 window tables: expected 63.75 mixed additions x 7 field products x 100 IMAD.WIDE + Barrett reduction (126) in "
+                    "ed25519_accumulate_kernel, 5 products + 1/8 inversion per signature in ed25519_finish_kernel; SHA-512 and the 19*g / 2*f "
+                    "pre-scalings (plain IMAD) not counted; the first K1b executed 134 970 per verification"}
         k3_bytes = ed["k3_items"] * (10 * (4 + 32) + 32 + 1)
         out["roofline_secondary"]["k3_lagrange"] = {
             "bound": "hbm", "achieved": k3_bytes / (ed["k3_kernel_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

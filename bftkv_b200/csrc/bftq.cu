@@ -7,7 +7,7 @@
 #include "tally.cuh"
 #include "lagrange.cuh"
 #include "modexp.cuh"
-#include "ed25519.cuh"
+#include "ed25519_fast.cuh"
 #include "p256.cuh"
 #include "dsa_verify.cuh"
 #include "pgp_digest.cuh"
@@ -172,8 +172,20 @@ struct PackerPool {
   }
 };
 
+// Ed25519 window-table cache (see ed_cache_prepare).
+struct EdCache {
+  std::mutex mu;
+  bftq::ed::gea* d_tab = nullptr;                // cap_slots x 4096 entries of 128 bytes
+  bftq::EdSlotHdr* d_hdr = nullptr;
+  uint32_t cap_slots = 0, used = 0;
+  uint64_t builds = 0;                           // slots built so far
+  std::map<std::string, uint32_t> slot_of;       // 32 key bytes -> slot
+  std::vector<cudaEvent_t> pending;              // builds that may still be running
+};
+
 struct bftq_engine {
   int device = 0;
+  EdCache ed;
   int sm_count = 0;
   std::mutex mu;
   std::vector<bftq::RsaKeyDev> h_keys;
@@ -613,6 +625,10 @@ void bftq_shutdown(bftq_engine* e) {
   }
   if (e->d_keys) cudaFree(e->d_keys);
   if (e->d_keys32) cudaFree(e->d_keys32);
+  cudaDeviceSynchronize();
+  for (cudaEvent_t ev : e->ed.pending) cudaEventDestroy(ev);
+  if (e->ed.d_tab) cudaFree(e->ed.d_tab);
+  if (e->ed.d_hdr) cudaFree(e->ed.d_hdr);
   for (void* p : e->retired) cudaFree(p);
   delete e;
 }
@@ -800,36 +816,121 @@ int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* 
 }
 
 // ---- K1b --------------------------------------------------------------------------------------
-int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* d_pubkeys, uint32_t n_keys, const uint32_t* d_key_idx,
+namespace {
+// Per-engine cache of Ed25519 window tables (ed25519_fast.cuh): slot 0 = the base point, slot s > 0 = -A of one key,
+// found by the 32 key bytes.  Slots are immutable once built and never move, so kernels of any stream may read them;
+// a slot built on one stream is ordered before readers on other streams by the build's event.  The cache is bounded
+// (BFTQ_ED25519_CACHE_SLOTS, default 256 = 128 MB): a batch whose new keys do not fit runs the table-free kernel.
+int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, cudaStream_t st, std::vector<uint32_t>& slot_of_key, bool& fits) {
+  EdCache& c = e->ed;
+  fits = false;
+  if (c.cap_slots == 0) {
+    uint32_t cap = 256;
+    if (const char* v = getenv("BFTQ_ED25519_CACHE_SLOTS")) cap = (uint32_t)std::max(2, atoi(v));
+    const size_t bytes = (size_t)cap * bftq::ed::kFxEntries * sizeof(bftq::ed::gea);
+    void* tab = nullptr; void* hdr = nullptr;
+    if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return BFTQ_OK; }          // no room: table-free kernel
+    if (cudaMalloc(&hdr, (size_t)cap * sizeof(bftq::EdSlotHdr)) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); return BFTQ_OK; }
+    CU(cudaMemset(hdr, 0, (size_t)cap * sizeof(bftq::EdSlotHdr)));
+    c.d_tab = (bftq::ed::gea*)tab; c.d_hdr = (bftq::EdSlotHdr*)hdr; c.cap_slots = cap; c.used = 0;
+  }
+  // which keys are new?
+  std::vector<std::string> fresh;
+  std::map<std::string, uint32_t> fresh_idx;
+  slot_of_key.assign(n_keys, 0);
+  const bool need_base = c.used == 0;
+  for (uint32_t i = 0; i < n_keys; i++) {
+    std::string kb((const char*)pubkeys + (size_t)i * 32, 32);
+    auto it = c.slot_of.find(kb);
+    if (it != c.slot_of.end()) { slot_of_key[i] = it->second; continue; }
+    auto f = fresh_idx.find(kb);
+    if (f == fresh_idx.end()) { f = fresh_idx.emplace(kb, (uint32_t)fresh.size()).first; fresh.push_back(kb); }
+    slot_of_key[i] = 0x80000000u | f->second;                 // resolved below
+  }
+  const uint32_t first = need_base ? 0u : c.used;
+  const uint32_t n_new = (uint32_t)fresh.size() + (need_base ? 1u : 0u);
+  if ((uint64_t)first + n_new > c.cap_slots) return BFTQ_OK;   // does not fit: caller takes the table-free kernel
+  // earlier builds on other streams must be complete before this stream reads their slots
+  for (size_t i = 0; i < c.pending.size();) {
+    if (cudaEventQuery(c.pending[i]) == cudaSuccess) { cudaEventDestroy(c.pending[i]); c.pending[i] = c.pending.back(); c.pending.pop_back(); }
+    else { cudaGetLastError(); CU(cudaStreamWaitEvent(st, c.pending[i], 0)); i++; }
+  }
+  if (n_new) {
+    const uint32_t key_slot0 = first + (need_base ? 1u : 0u);
+    if (!fresh.empty()) {
+      std::vector<bftq::EdSlotHdr> h(fresh.size());
+      for (size_t i = 0; i < fresh.size(); i++) { memset(&h[i], 0, sizeof(h[i])); memcpy(h[i].key, fresh[i].data(), 32); }
+      CU(cudaMemcpyAsync(c.d_hdr + key_slot0, h.data(), h.size() * sizeof(bftq::EdSlotHdr), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    }
+    bftq::ed::gex* d_bases = nullptr;
+    CU(cudaMallocAsync((void**)&d_bases, (size_t)n_new * bftq::ed::kFxWindows * sizeof(bftq::ed::gex), st));
+    bftq::ed25519_bases_kernel<<<(n_new + 31) / 32, 32, 0, st>>>(c.d_hdr, first, n_new, d_bases);
+    const uint64_t threads = (uint64_t)n_new * bftq::ed::kFxWindows * (bftq::ed::kFxMultiples / bftq::ed::kFxChunk);
+    bftq::ed25519_multiples_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_bases, first, n_new, c.d_tab);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_bases, st));
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, st));
+    c.pending.push_back(ev);
+    for (size_t i = 0; i < fresh.size(); i++) c.slot_of.emplace(fresh[i], key_slot0 + (uint32_t)i);
+    c.used = first + n_new;
+    c.builds += n_new;
+  }
+  for (uint32_t i = 0; i < n_keys; i++) if (slot_of_key[i] & 0x80000000u) slot_of_key[i] = c.slot_of[fresh[slot_of_key[i] & 0x7fffffffu]];
+  fits = true;
+  return BFTQ_OK;
+}
+}  // namespace
+
+int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* d_key_idx,
                                   const uint8_t* d_sig, const uint8_t* d_msg, uint64_t n_items, uint8_t* d_status,
                                   void* cuda_stream) {
-  if (!e || !d_pubkeys || !d_key_idx || !d_sig || !d_msg || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
+  if (!e || !pubkeys || !d_key_idx || !d_sig || !d_msg || !d_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (n_items == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
-  const int block = 128;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  // Signatures that share keys (OpenPGP: a handful of keys, many signatures) pay the doublings once per key: window
-  // tables for -A of every key and for the base point (82 KB each, stream-ordered scratch), then at most 128 table
-  // additions per signature.  With few signatures per key the classic double-and-add kernel is cheaper.
+  // Signatures that share keys (OpenPGP: a handful of keys, many signatures) run against the cached window tables: at most
+  // 64 mixed additions per signature and no doubling.  With few signatures per key (a table costs about 400
+  // verifications' worth of work, once per key and engine) the table-free double-and-add kernel is used.
   static const bool no_tables = [] { const char* v = getenv("BFTQ_ED25519_TABLES"); return v && atoi(v) == 0; }();
-  const bool windowed = !no_tables && n_keys > 0 && n_keys <= 4096 && n_items >= 64ull * ((uint64_t)n_keys + 1);
-  int launches = 1;
-  if (windowed) {
-    bftq::ed::gec* d_tab = nullptr;
-    uint8_t* d_ok = nullptr;
-    const size_t tab_bytes = ((size_t)n_keys + 1) * bftq::ed::kEdTableEntries * sizeof(bftq::ed::gec);
-    CU(cudaMallocAsync((void**)&d_tab, tab_bytes + n_keys, st));
-    d_ok = reinterpret_cast<uint8_t*>(d_tab) + tab_bytes;
-    bftq::ed25519_table_kernel<<<n_keys + 1, 64, 0, st>>>(d_pubkeys, n_keys, d_tab, d_ok);
-    bftq::ed25519_verify_windowed_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(
-        d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_tab, d_ok, d_status);
+  bool tables = !no_tables && n_keys > 0 && n_keys <= 4096 && n_items >= 128ull * ((uint64_t)n_keys + 1);
+  int launches = 0;
+  if (tables) {
+    std::vector<uint32_t> slot_of_key;
+    std::lock_guard<std::mutex> g(e->ed.mu);                   // held while this call's work is enqueued
+    const uint64_t before = e->ed.builds;
+    const int rc = ed_cache_prepare(e, pubkeys, n_keys, st, slot_of_key, tables);
+    if (rc) return rc;
+    if (tables) {
+      launches += e->ed.builds != before ? 2 : 0;
+      const uint64_t n_pad = (n_items + 511) / 512 * 512;
+      const size_t xyz_bytes = (size_t)n_pad * 30 * sizeof(int32_t);
+      const size_t slot_bytes = ((size_t)n_keys * 4 + 15) / 16 * 16;
+      uint8_t* scratch = nullptr;
+      CU(cudaMallocAsync((void**)&scratch, xyz_bytes + slot_bytes + n_pad, st));
+      int32_t* d_xyz = reinterpret_cast<int32_t*>(scratch);
+      uint32_t* d_slot = reinterpret_cast<uint32_t*>(scratch + xyz_bytes);
+      uint8_t* d_pre = scratch + xyz_bytes + slot_bytes;
+      CU(cudaMemcpyAsync(d_slot, slot_of_key.data(), (size_t)n_keys * 4, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+      bftq::ed25519_accumulate_kernel<<<(unsigned)((n_items + bftq::kEdAccBlock - 1) / bftq::kEdAccBlock), bftq::kEdAccBlock, 0, st>>>(
+          e->ed.d_tab, e->ed.d_hdr, d_slot, n_keys, d_key_idx, d_sig, d_msg, n_items, n_pad, d_xyz, d_pre);
+      const uint64_t fin_threads = n_pad / bftq::ed::kFxChunk;
+      bftq::ed25519_finish_kernel<<<(unsigned)(fin_threads / bftq::kEdFinBlock), bftq::kEdFinBlock, 0, st>>>(d_xyz, d_pre, d_sig, n_items, n_pad, d_status);
+      CU(cudaGetLastError());
+      CU(cudaFreeAsync(scratch, st));
+      launches += 2;
+    }
+  }
+  if (!tables) {
+    uint8_t* d_pk = nullptr;
+    CU(cudaMallocAsync((void**)&d_pk, (size_t)std::max<uint32_t>(n_keys, 1) * 32, st));
+    if (n_keys) CU(cudaMemcpyAsync(d_pk, pubkeys, (size_t)n_keys * 32, cudaMemcpyHostToDevice, st));
+    const int block = 128;
+    bftq::ed25519_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(d_pk, n_keys, d_key_idx, d_sig, d_msg, n_items, d_status);
     CU(cudaGetLastError());
-    CU(cudaFreeAsync(d_tab, st));
-    launches = 2;
-  } else {
-    bftq::ed25519_verify_kernel<<<(unsigned)((n_items + block - 1) / block), block, 0, st>>>(
-        d_pubkeys, n_keys, d_key_idx, d_sig, d_msg, n_items, d_status);
-    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_pk, st));
+    launches = 1;
   }
   std::lock_guard<std::mutex> g(e->mu);
   e->stats.launches += launches;
@@ -842,15 +943,14 @@ int bftq_ed25519_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n
   if (!e || !pubkeys || !key_idx || !sig || !msg || !out_status) return fail(BFTQ_ERR_INVALID_ARG, "NULL argument");
   if (n_items == 0) return BFTQ_OK;
   Arena a(e);
-  uint8_t *d_pk, *d_sig, *d_msg, *d_st; uint32_t* d_idx;
-  a.in(&d_pk, pubkeys, (size_t)std::max<uint32_t>(n_keys, 1) * 32, (size_t)n_keys * 32);
+  uint8_t *d_sig, *d_msg, *d_st; uint32_t* d_idx;
   a.in(&d_idx, key_idx, (size_t)n_items);
   a.in(&d_sig, sig, (size_t)n_items * 64);
   a.in(&d_msg, msg, (size_t)n_items * 32);
   a.out(&d_st, out_status, (size_t)n_items);
   int rc = a.upload();
   if (rc) return rc;
-  rc = bftq_ed25519_verify_batch_dev(e, d_pk, n_keys, d_idx, d_sig, d_msg, n_items, d_st, a.stream());
+  rc = bftq_ed25519_verify_batch_dev(e, pubkeys, n_keys, d_idx, d_sig, d_msg, n_items, d_st, a.stream());
   if (rc) return rc;
   return a.download();
 }

@@ -9,6 +9,8 @@
 // In OpenPGP (RFC 4880bis / GnuPG) M is the 32-byte v4 signature digest, so messages are a fixed 32
 // bytes here.  Parity oracle for this kernel: libsodium (pynacl) and OpenSSL (`cryptography`).
 //
+// This file: the table-free kernel (batches with few signatures per key) and the shared field / group / scalar code;
+// ed25519_fast.cuh holds the cached-window-table path every large batch takes.
 // One thread per signature; field elements are 10 limbs in radix 2^25.5 (26/25-bit alternating,
 // signed) so that every product is one 32x32->64 IMAD.WIDE and ten of them are summed without
 // carries — the same lazy-carry idea as K1's radix-2^28 kernel, in the form curve25519 code has
@@ -272,25 +274,60 @@ BFTQ_HD void ge_tobytes(uint8_t* s, const ge& p) {
 }
 
 // ---- scalars mod L ------------------------------------------------------------------------------
-// out (8 words) = the 64-byte little-endian value `in` mod L (bitwise shift-subtract; 512 steps).
-BFTQ_HD_NOINLINE void sc_reduce64(uint32_t (&out)[8], const uint8_t* in) {
-  const uint32_t Lw[8] = BFTQ_ED_L;
-  uint32_t r[9];
-  for (int i = 0; i < 9; i++) r[i] = 0;
-  for (int byte = 63; byte >= 0; byte--) {
-    for (int bit = 7; bit >= 0; bit--) {
-      uint32_t c = (in[byte] >> bit) & 1u;
-      for (int i = 0; i < 9; i++) { const uint32_t nc = r[i] >> 31; r[i] = (r[i] << 1) | c; c = nc; }
-      bool ge = r[8] != 0;
-      if (!ge) { ge = true; for (int i = 7; i >= 0; i--) { if (r[i] != Lw[i]) { ge = r[i] > Lw[i]; break; } } }
-      if (ge) {
-        uint32_t br = 0;
-        for (int i = 0; i < 8; i++) { const uint64_t d = (uint64_t)r[i] - Lw[i] - br; r[i] = (uint32_t)d; br = (uint32_t)(d >> 63); }
-        r[8] -= br;
-      }
+// ---- scalars: Barrett reduction mod L (HAC 14.42 with b = 2^32, k = 8) -----------------------------------------------
+// out = x mod L for the 512-bit x given as 16 little-endian words.
+BFTQ_HD_NOINLINE void sc_reduce512(uint32_t (&out)[8], const uint32_t (&x)[16]) {
+  const uint32_t Lw[9] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0x0u, 0x0u, 0x0u, 0x10000000u, 0u};
+  const uint32_t mu[9] = {0x0a2c131bu, 0xed9ce5a3u, 0x086329a7u, 0x2106215du, 0xffffffebu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfu};  // floor(2^512 / L)
+  uint32_t q2[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) q2[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {                              // q2 = floor(x / b^7) * mu
+    uint64_t carry = 0;
+    const uint32_t qi = x[7 + i];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      const uint64_t acc = (uint64_t)q2[i + j] + (uint64_t)qi * mu[j] + carry;
+      q2[i + j] = (uint32_t)acc; carry = acc >> 32;
+    }
+    q2[i + 9] = (uint32_t)carry;
+  }
+  uint32_t r2[9];                                            // r2 = (floor(q2 / b^9) * L) mod b^9
+#pragma unroll
+  for (int i = 0; i < 9; i++) r2[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    uint64_t carry = 0;
+    const uint32_t qi = q2[9 + i];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      if (j + i >= 9) continue;
+      const uint64_t acc = (uint64_t)r2[i + j] + (uint64_t)qi * Lw[j] + carry;
+      r2[i + j] = (uint32_t)acc; carry = acc >> 32;
+    }
+  }
+  uint32_t r[9];                                             // r = (x mod b^9) - r2 mod b^9, then at most two subtractions of L
+  uint32_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { const uint64_t d = (uint64_t)x[i] - r2[i] - br; r[i] = (uint32_t)d; br = (uint32_t)(d >> 63); }
+  for (int pass = 0; pass < 2; pass++) {
+    bool ge = true, decided = false;                         // r >= L ?
+#pragma unroll
+    for (int i = 8; i >= 0; i--) { if (!decided && r[i] != Lw[i]) { ge = r[i] > Lw[i]; decided = true; } }
+    if (ge) {
+      uint32_t b2 = 0;
+#pragma unroll
+      for (int i = 0; i < 9; i++) { const uint64_t d = (uint64_t)r[i] - Lw[i] - b2; r[i] = (uint32_t)d; b2 = (uint32_t)(d >> 63); }
     }
   }
   for (int i = 0; i < 8; i++) out[i] = r[i];
+}
+// out (8 words) = the 64-byte little-endian value `in` mod L.
+BFTQ_HD void sc_reduce64(uint32_t (&out)[8], const uint8_t* in) {
+  uint32_t x[16];
+  for (int i = 0; i < 16; i++) x[i] = (uint32_t)in[4 * i] | ((uint32_t)in[4 * i + 1] << 8) | ((uint32_t)in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24);
+  sc_reduce512(out, x);
 }
 // s (32 bytes little-endian) < L ?
 BFTQ_HD bool sc_is_canonical(const uint8_t* s, uint32_t (&w)[8]) {
@@ -324,76 +361,6 @@ BFTQ_HD bool verify_core(const uint8_t* sig, const uint8_t* pk, const uint32_t (
   return diff == 0;
 }
 
-
-// ---- per-key window tables: [S]B - [k]A without a single doubling -------------------------------------------
-// A batch of OpenPGP signatures is signed by a handful of keys (BASELINE configs[3]: 262 144 signatures, 15 keys),
-// so the doublings of the double-scalar multiplication can be paid once per KEY instead of once per signature:
-// for the base point and for every -A the table holds j * 16^i * P (i = 0..63, j = 1..8) in cached form, the
-// scalars are recoded to 64 signed radix-16 digits, and a verification is at most 128 table additions
-// (~1 000 field products) instead of 253 doublings + ~190 additions (~3 500).
-struct gec { fe YpX, YmX, Z, T2d; };            // (Y+X, Y-X, Z, 2dT), every limb carried: safe as fe_mul's SECOND operand
-constexpr int kEdWindows = 64, kEdMultiples = 8;
-constexpr int kEdTableEntries = kEdWindows * kEdMultiples;
-
-BFTQ_HD void fe_carried_add(fe h, const fe f, const fe g) { int64_t t[10]; for (int i = 0; i < 10; i++) t[i] = (int64_t)f[i] + g[i]; fe_carry(h, t); }
-BFTQ_HD void fe_carried_sub(fe h, const fe f, const fe g) { int64_t t[10]; for (int i = 0; i < 10; i++) t[i] = (int64_t)f[i] - g[i]; fe_carry(h, t); }
-BFTQ_HD void ge_to_cached(gec& c, const ge& p) {
-  fe_carried_add(c.YpX, p.Y, p.X); fe_carried_sub(c.YmX, p.Y, p.X);
-  fe_copy(c.Z, p.Z);
-  fe_mul(c.T2d, p.T, BFTQ_ED_TAB(kD2));
-}
-// r = p + q (neg: p - q).  r may alias p.
-BFTQ_HD_NOINLINE void ge_add_cached(ge& r, const ge& p, const gec& q, const bool neg) {
-  fe a, b, c, d, e, f, g, h, t;
-  fe_add(t, p.Y, p.X); fe_mul(a, t, neg ? q.YmX : q.YpX);
-  fe_sub(t, p.Y, p.X); fe_mul(b, t, neg ? q.YpX : q.YmX);
-  fe_mul(c, p.T, q.T2d);
-  if (neg) fe_neg(c, c);
-  fe_mul(d, p.Z, q.Z); fe_add(d, d, d);
-  fe_sub(e, a, b); fe_add(h, a, b); fe_add(g, d, c); fe_sub(f, d, c);
-  fe_mul(r.X, e, f); fe_mul(r.Y, g, h); fe_mul(r.T, e, h); fe_mul(r.Z, f, g);
-}
-// Window i of P's table: out[j-1] = j * 16^i * P, j = 1..8.
-BFTQ_HD void ge_window_multiples(gec* out, const ge& P, const int window) {
-  ge base = P;
-  for (int t = 0; t < 4 * window; t++) { ge d; ge_dbl(d, base); base = d; }
-  ge m = base;
-  ge_to_cached(out[0], m);
-  for (int j = 1; j < kEdMultiples; j++) { ge n; ge_add(n, m, base); m = n; ge_to_cached(out[j], m); }
-}
-BFTQ_HD void ge_basepoint(ge& b) { fe_copy(b.X, BFTQ_ED_TAB(kBx)); fe_copy(b.Y, BFTQ_ED_TAB(kBy)); fe_1(b.Z); fe_copy(b.T, BFTQ_ED_TAB(kBt)); }
-// 64 signed radix-16 digits in [-8, 8] of a scalar < 2^253 given as 8 little-endian words (ref10's recoding).
-BFTQ_HD void sc_signed_digits(int8_t (&e)[64], const uint32_t (&w)[8]) {
-  for (int i = 0; i < 64; i++) e[i] = (int8_t)((w[i >> 3] >> (4 * (i & 7))) & 15u);
-  int carry = 0;
-  for (int i = 0; i < 63; i++) {
-    e[i] = (int8_t)(e[i] + carry);
-    carry = (e[i] + 8) >> 4;
-    e[i] = (int8_t)(e[i] - (carry << 4));
-  }
-  e[63] = (int8_t)(e[63] + carry);
-}
-// encode([S]B - [k]A) == R with the two window tables (tabB for B, tabNegA for -A).  S canonical is checked here;
-// the caller has checked that A decodes (its table exists).
-BFTQ_HD bool verify_windowed(const uint8_t* sig, const uint32_t (&k)[8], const gec* tabB, const gec* tabNegA) {
-  uint32_t s[8];
-  if (!sc_is_canonical(sig + 32, s)) return false;                 // S >= L
-  int8_t es[64], ek[64];
-  sc_signed_digits(es, s);
-  sc_signed_digits(ek, k);
-  ge p;
-  ge_identity(p);
-  for (int i = 0; i < kEdWindows; i++) {
-    const int ds = es[i], dk = ek[i];
-    if (ds) { const gec q = tabB[i * kEdMultiples + (ds < 0 ? -ds : ds) - 1]; ge_add_cached(p, p, q, ds < 0); }
-    if (dk) { const gec q = tabNegA[i * kEdMultiples + (dk < 0 ? -dk : dk) - 1]; ge_add_cached(p, p, q, dk < 0); }
-  }
-  uint8_t enc[32];
-  ge_tobytes(enc, p);
-  uint8_t diff = 0;
-  for (int i = 0; i < 32; i++) diff |= enc[i] ^ sig[i];
-  return diff == 0;
-}
 
 }}  // namespace bftq::ed
 
@@ -437,61 +404,5 @@ ed25519_verify_kernel(const uint8_t* __restrict__ pubkeys, const uint32_t n_keys
   status[item] = ed::verify_core(s, a, k) ? 0 : 1;
 }
 
-// k = SHA-512(R || A || M) mod L for one item (96 bytes = one padded block).
-__device__ __forceinline__ void ed25519_hram(uint32_t (&k)[8], const uint8_t* s, const uint8_t* a, const uint8_t* m) {
-  uint64_t w[16];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    uint64_t r = 0, aa = 0, mm = 0;
-#pragma unroll
-    for (int b = 0; b < 8; b++) { r = (r << 8) | s[8 * i + b]; aa = (aa << 8) | a[8 * i + b]; mm = (mm << 8) | (uint64_t)__ldg(m + 8 * i + b); }
-    w[i] = r; w[4 + i] = aa; w[8 + i] = mm;
-  }
-  w[12] = 0x8000000000000000ull; w[13] = 0; w[14] = 0;
-  w[15] = 96 * 8;
-  uint64_t h[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
-                   0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
-  sha512_compress(h, w);
-  uint8_t dg[64];
-  for (int i = 0; i < 8; i++) for (int b = 0; b < 8; b++) dg[8 * i + b] = (uint8_t)(h[i] >> (56 - 8 * b));
-  ed::sc_reduce64(k, dg);
-}
-
-// Window tables: block = one point (keys 0..n_keys-1: -A_key; block n_keys: the base point), thread = one window.
-// key_ok[key] = 0 when A does not decode (RFC 8032 §5.1.3): every signature under that key is invalid.
-__global__ void __launch_bounds__(64)
-ed25519_table_kernel(const uint8_t* __restrict__ pubkeys, const uint32_t n_keys, ed::gec* __restrict__ tables, uint8_t* __restrict__ key_ok) {
-  const uint32_t key = blockIdx.x;
-  const int window = threadIdx.x;
-  ed::ge P;
-  if (key == n_keys) ed::ge_basepoint(P);
-  else {
-    uint8_t a[32];
-    for (int i = 0; i < 32; i++) a[i] = __ldg(pubkeys + (uint64_t)key * 32 + i);
-    const bool ok = ed::ge_frombytes(P, a);
-    if (window == 0) key_ok[key] = ok ? 1 : 0;
-    if (!ok) return;
-    ed::ge_neg(P, P);
-  }
-  ed::ge_window_multiples(tables + ((size_t)key * ed::kEdWindows + window) * ed::kEdMultiples, P, window);
-}
-
-// One thread per signature against the window tables: no doublings (see ed::verify_windowed).
-__global__ void __launch_bounds__(128)
-ed25519_verify_windowed_kernel(const uint8_t* __restrict__ pubkeys, const uint32_t n_keys, const uint32_t* __restrict__ key_idx,
-                               const uint8_t* __restrict__ sig, const uint8_t* __restrict__ msg, const uint64_t n_items,
-                               const ed::gec* __restrict__ tables, const uint8_t* __restrict__ key_ok, uint8_t* __restrict__ status) {
-  const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= n_items) return;
-  const uint32_t kidx = __ldg(key_idx + item);
-  if (kidx >= n_keys) { status[item] = 4; return; }
-  if (!key_ok[kidx]) { status[item] = 1; return; }
-  uint8_t s[64], a[32];
-  for (int i = 0; i < 64; i++) s[i] = __ldg(sig + item * 64 + i);
-  for (int i = 0; i < 32; i++) a[i] = __ldg(pubkeys + (uint64_t)kidx * 32 + i);
-  uint32_t k[8];
-  ed25519_hram(k, s, a, msg + item * 32);
-  status[item] = ed::verify_windowed(s, k, tables + (size_t)n_keys * ed::kEdTableEntries, tables + (size_t)kidx * ed::kEdTableEntries) ? 0 : 1;
-}
 }  // namespace bftq
 #endif

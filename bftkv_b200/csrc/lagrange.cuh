@@ -9,9 +9,9 @@
 // panics; here the item gets status BFTQ_ST_MALFORMED).
 //
 // One thread per combine, L 32-bit limbs (L = 8 covers the 160-bit DSA q and the P-256 order,
-// L = 64 the 2048-bit modulus of sss_test.go).  Every factor (x_j - x_i) is a small integer d; its
-// inverse is  (1 + m*t)/d  with  t = (-m^-1) mod d  from a 64-bit extended Euclid — no big-number
-// inversion at all.  Products run in Montgomery form (m must be odd); y_i may be >= m (the
+// L = 64 the 2048-bit modulus of sss_test.go).  Every factor (x_j - x_i) is a small integer; products of
+// them that still fit 32 bits are inverted together: the inverse of d is  (1 + m*t)/d  with  t = (-m^-1) mod d
+// from a 64-bit extended Euclid — no big-number inversion at all.  Products run in Montgomery form (m must be odd); y_i may be >= m (the
 // reference's big.Int arithmetic reduces it implicitly) as long as it fits mlen bytes.  HBM-bound: k*(4+mlen)+mlen
 // bytes per combine.
 #pragma once
@@ -129,28 +129,16 @@ __device__ bool small_inverse(uint32_t* inv, uint32_t d, const LagrangeMod<L>& M
   return true;
 }
 
-// x mod m as a plain big number, x a signed 32-bit integer.
+// mag mod m as a plain big number (mag < 2^32).
 template <int L>
-__device__ void small_to_big(uint32_t* out, int32_t x, const LagrangeMod<L>& M) {
+__device__ void mag_to_big(uint32_t* out, const uint32_t mag, const LagrangeMod<L>& M) {
 #pragma unroll
   for (int i = 0; i < L; i++) out[i] = 0;
-  out[0] = (uint32_t)(x < 0 ? -(int64_t)x : (int64_t)x);
-  // reduce for tiny moduli (m may be smaller than |x|)
-  bool tiny = true;
+  out[0] = mag;
+  bool tiny = true;                       // m may be smaller than the chunk
 #pragma unroll
   for (int i = 1; i < L; i++) tiny = tiny && (M.m[i] == 0);
   if (tiny) out[0] %= M.m[0];
-  if (x < 0) {
-    bool zero = out[0] == 0;
-    if (!zero) {           // m - |x|
-      uint32_t tmp[L];
-#pragma unroll
-      for (int i = 0; i < L; i++) tmp[i] = M.m[i];
-      sub_big<L>(tmp, out);
-#pragma unroll
-      for (int i = 0; i < L; i++) out[i] = tmp[i];
-    }
-  }
 }
 
 template <int L>
@@ -171,29 +159,60 @@ lagrange_combine_kernel(const LagrangeMod<L> M, const uint32_t k, const int32_t*
     uint32_t lam[L];
 #pragma unroll
     for (int l = 0; l < L; l++) lam[l] = M.r1[l];               // 1 in Montgomery form
-    for (uint32_t j = 0; j < k; j++) {
-      const int32_t xj = __ldg(x + j);
-      if (xj == xi) continue;                                    // sss.go:100-102 (also skips duplicates)
-      const int64_t d = (int64_t)xj - (int64_t)xi;
-      uint32_t tmp[L];
-      const uint64_t ad = (uint64_t)(d < 0 ? -d : d);
-      if (ad >> 32) { okay = false; continue; }
-      if (!small_inverse<L>(tmp, (uint32_t)ad, M)) { okay = false; continue; }
-      if (d < 0) {                                               // inverse of a negative: m - inv
-        uint32_t neg[L];
-#pragma unroll
-        for (int l = 0; l < L; l++) neg[l] = M.m[l];
-        sub_big<L>(neg, tmp);
-#pragma unroll
-        for (int l = 0; l < L; l++) tmp[l] = neg[l];
-        if (ge_big<L>(tmp, M.m)) sub_big<L>(tmp, M.m);           // inv == 0 cannot happen; keeps tmp < m
+    // Factors are gathered into 32-bit chunks before they touch a big number: numerator chunks |x_j| * |x_j'| * ... and
+    // denominator chunks |x_j - x_i| * ..., each flushed (one small-integer inverse / one lift to Montgomery form, one
+    // product into lambda) only when the next factor would overflow 2^32.  With node indices as abscissae (1..n, k = 10)
+    // that is one or two inversions and about eight Montgomery products per lambda instead of nine and thirty-six.  The
+    // value is the same residue: gcd(ab, m) = 1 iff gcd(a, m) = gcd(b, m) = 1, so the "no inverse" decision is too.
+    uint32_t numc = 1u, denc = 1u;
+    bool neg = false;
+    for (uint32_t j = 0; j <= k; j++) {
+      const bool last = j == k;
+      uint32_t ax = 1u, ad32 = 1u;
+      if (!last) {
+        const int32_t xj = __ldg(x + j);
+        if (xj == xi) continue;                                  // sss.go:100-102 (also skips duplicates)
+        const int64_t d = (int64_t)xj - (int64_t)xi;
+        const uint64_t ad = (uint64_t)(d < 0 ? -d : d);
+        if (ad >> 32) { okay = false; continue; }
+        neg ^= (d < 0) != (xj < 0);
+        ax = (uint32_t)(xj < 0 ? -(int64_t)xj : (int64_t)xj);
+        ad32 = (uint32_t)ad;
       }
-      // lam stays in Montgomery form: each plain factor is lifted with R^2 first
-      mont_mul_big<L>(tmp, tmp, M.r2, M);
-      mont_mul_big<L>(lam, lam, tmp, M);
-      small_to_big<L>(tmp, xj, M);
-      mont_mul_big<L>(tmp, tmp, M.r2, M);
-      mont_mul_big<L>(lam, lam, tmp, M);
+      const uint64_t pn = (uint64_t)numc * ax, pd = (uint64_t)denc * ad32;
+      if (last || (pn >> 32)) {                                  // flush the numerator chunk
+        if (numc != 1u) {
+          uint32_t tmp[L];
+          mag_to_big<L>(tmp, numc, M);
+          mont_mul_big<L>(tmp, tmp, M.r2, M);
+          mont_mul_big<L>(lam, lam, tmp, M);
+        }
+        numc = ax;
+      } else numc = (uint32_t)pn;
+      if (last || (pd >> 32)) {                                  // flush the denominator chunk
+        if (denc != 1u) {
+          uint32_t tmp[L];
+          if (!small_inverse<L>(tmp, denc, M)) okay = false;
+          else {
+            mont_mul_big<L>(tmp, tmp, M.r2, M);
+            mont_mul_big<L>(lam, lam, tmp, M);
+          }
+        }
+        denc = ad32;
+      } else denc = (uint32_t)pd;
+    }
+    if (neg) {                                                   // an odd number of negative factors: lambda -> m - lambda
+      bool zero = true;
+#pragma unroll
+      for (int l = 0; l < L; l++) zero = zero && (lam[l] == 0u);
+      if (!zero) {
+        uint32_t t2[L];
+#pragma unroll
+        for (int l = 0; l < L; l++) t2[l] = M.m[l];
+        sub_big<L>(t2, lam);
+#pragma unroll
+        for (int l = 0; l < L; l++) lam[l] = t2[l];
+      }
     }
     if (out_lambda != nullptr) {                                 // lambda_i itself (plain), k x mlen bytes per item
       uint32_t one[L], lp[L];

@@ -312,8 +312,14 @@ struct RsaKey32 {               // per key, radix 2^32 little-endian words
   uint32_t pad;
 };
 
+// In-block barriers that keep the four warps of a block in phase (see the kernel's task loop).  Measured on B200
+// (gpurun_out -> profiles/k1_sync_variants_r02.txt, 65 536 / 524 288 items, two streams): 0 = none 53.2 / 46.9 M verifies/s,
+// 1 = once per task 56.0 / 57.0, 2 = after every Montgomery product 58.0 / 58.0, 3 = 2 + every owner step 58.0 / 58.0.
+// Warps that drift apart fetch different parts of the 15 KB hot loop and evict each other from the instruction caches
+// (the long-batch rate of the barrier-free kernel DROPS, 44.8 M/s on one stream); a barrier per product costs 18
+// bar.sync per 2.3 M instructions.
 #ifndef BFTQ_K1_SYNC
-#define BFTQ_K1_SYNC 0
+#define BFTQ_K1_SYNC 2
 #endif
 // SQ: the squarings of the exponentiation go through mont_sqr (rsa_square_r32.cuh) instead of mont_mul(y, y).
 template <int BLOCK, int MIN_BLOCKS, bool SQ>

@@ -117,22 +117,105 @@ def test_rfc8032_vectors_and_openssl(host):
         assert host.ed_verify_core_host(s0, badpk, hashlib.sha512(s0[:32] + badpk + m0).digest()) == 0
 
 
-def test_windowed_core_equals_classic_core(host):
-    """The per-key window-table verification (what the batch kernel runs when signatures share keys) against the
-    classic double-and-add core, OpenSSL and the RFC 8032 vectors: valid, bit-flipped, S >= L, undecodable A,
-    small-order A and R, and scalars whose signed digits carry all the way up."""
-    import ctypes
-    host.ed_signed_digits_host.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
-    rng = random.Random(11)
-    for _ in range(300):                                  # the recoding: sum e_i 16^i == s, e_i in [-8, 8]
-        s = rng.choice([rng.randrange(L), L - 1, 0, 1, 2 ** 252, int("8" * 63, 16) % L, int("7" * 63, 16), 2 ** 252 + 2 ** 251])
-        buf = ctypes.create_string_buffer(64)
-        host.ed_signed_digits_host(s.to_bytes(32, "little"), buf)
-        digs = [b - 256 if b > 127 else b for b in buf.raw]
-        assert all(-8 <= d <= 8 for d in digs) and sum(d * 16 ** i for i, d in enumerate(digs)) == s
+D = -121665 * pow(121666, -1, P) % P
+
+
+def _edwards_add(p, q):
+    (x1, y1), (x2, y2) = p, q
+    t = D * x1 * x2 * y1 * y2 % P
+    return ((x1 * y2 + x2 * y1) * pow(1 + t, -1, P) % P, (y1 * y2 + x1 * x2) * pow(1 - t, -1, P) % P)
+
+
+def _edwards_mul(k, p):
+    r = (0, 1)
+    while k:
+        if k & 1:
+            r = _edwards_add(r, p)
+        p = _edwards_add(p, p)
+        k >>= 1
+    return r
+
+
+def _decode_point(b):
+    y = int.from_bytes(b, "little") & ((1 << 255) - 1)
+    sign = b[31] >> 7
+    x2 = (y * y - 1) * pow(D * y * y + 1, -1, P) % P
+    x = pow(x2, (P + 3) // 8, P)
+    if (x * x - x2) % P:
+        x = x * pow(2, (P - 1) // 4, P) % P
+    assert (x * x - x2) % P == 0
+    if x & 1 != sign:
+        x = P - x
+    return (x, y)
+
+
+def test_fast_field_scalar_and_tables(host):
+    """ed25519_fast.cuh on the host: inlined product / squaring (carried and uncarried operands at the documented bounds),
+    the addition-chain powers, canonical words, the Barrett reduction mod L, the signed radix-256 recoding, and window-table
+    entries against big-integer Edwards arithmetic (affine y+x, y-x, 2dxy; limbs carried)."""
+    rng = random.Random(2)
+    out = ctypes.create_string_buffer(64)
+    b = lambda x: int(x).to_bytes(32, "little")
+    for i in range(2000):
+        x, y = rng.randrange(P), rng.randrange(P)
+        if i % 50 == 0:
+            x = P - 1
+        if i % 77 == 0:
+            y = P - 1 - (i % 3)
+        if i % 91 == 0:
+            x = 2 ** 255 - 20                              # non-canonical input representative
+        host.ed_fex_mul_host(b(x), b(y), out)
+        assert int.from_bytes(out.raw[:32], "little") == x * y % P
+        host.ed_fex_sq_host(b(x), out)
+        assert int.from_bytes(out.raw[:32], "little") == x * x % P
+        host.ed_fex_uncarried_host(b(x), b(y), out)
+        assert int.from_bytes(out.raw[:32], "little") == (x + y) ** 2 % P and int.from_bytes(out.raw[32:], "little") == (x + y) * (x - y) % P
+        host.ed_fex_towords_host(b(x), b(y), out)
+        assert int.from_bytes(out.raw[:32], "little") == x * y % P
+    for _ in range(40):
+        x = rng.randrange(1, P)
+        host.ed_fex_pow_host(b(x), 1, out)
+        assert int.from_bytes(out.raw[:32], "little") == pow(x, P - 2, P)
+        host.ed_fex_pow_host(b(x), 0, out)
+        assert int.from_bytes(out.raw[:32], "little") == pow(x, (P - 5) // 8, P)
+    edge = [bytes(64), b"\xff" * 64, L.to_bytes(32, "little") + bytes(32), (L - 1).to_bytes(32, "little") + bytes(32), (L * 2 ** 259).to_bytes(64, "little"),
+            (L * 2 ** 259 - 1).to_bytes(64, "little"), (2 ** 252).to_bytes(64, "little"), (L << 200).to_bytes(64, "little"), (2 ** 511).to_bytes(64, "little")]
+    near = [(rng.randrange(2 ** 259) * L + rng.choice([0, 1, L - 1, L - 2])).to_bytes(64, "little") for _ in range(500)]
+    for v in edge + near + [os.urandom(64) for _ in range(2000)]:
+        host.ed_sc_reduce512_host(v, out)
+        assert int.from_bytes(out.raw[:32], "little") == int.from_bytes(v, "little") % L, v.hex()
+    dg = (ctypes.c_int32 * 32)()
+    for _ in range(500):                                   # sum d_i 256^i == s, d_i in [-128, 127]
+        sc = rng.choice([rng.randrange(L), L - 1, 0, 1, 2 ** 252, int("80" * 31, 16), int("7f" * 31, 16), int("ff" * 31, 16), 2 ** 252 + 2 ** 251,
+                         int("1f" + "ff" * 31, 16)])
+        host.ed_digits256_host(sc.to_bytes(32, "little"), dg)
+        assert all(-128 <= v <= 127 for v in dg) and sum(v * 256 ** i for i, v in enumerate(dg)) == sc
+    # 3 P through gex_dbl / gex_add / the inversion chain
+    sks, pks, *_ = make_sigs(1, 3, 21)
+    for pk in pks:
+        assert host.ed_gex_roundtrip_host(pk, out) == 1
+        x3, y3 = _edwards_mul(3, _decode_point(pk))
+        assert int.from_bytes(out.raw[:32], "little") == y3 | ((x3 & 1) << 255)
+    # table entries of a key: j * 256^w * A
+    A = _decode_point(pks[0])
+    e1, e2, e3 = (ctypes.create_string_buffer(32) for _ in range(3))
+    for w, j in [(0, 1), (0, 2), (0, 8), (0, 9), (0, 128), (1, 1), (1, 77), (5, 121), (17, 64), (31, 1), (31, 31), (31, 128)] + \
+                [(rng.randrange(32), rng.randrange(1, 129)) for _ in range(20)]:
+        assert host.ed_fx_table_entry_host(pks[0], w, j, e1, e2, e3) == 1, "entry not carried"
+        x, y = _edwards_mul(j * 256 ** w, A)
+        assert int.from_bytes(e1.raw, "little") == (y + x) % P and int.from_bytes(e2.raw, "little") == (y - x) % P
+        assert int.from_bytes(e3.raw, "little") == 2 * D * x * y % P
+
+
+def test_fast_core_equals_classic_core(host):
+    """The cached-window-table verification (what the batch kernels run when signatures share keys: accumulate + finish)
+    against the classic double-and-add core, OpenSSL and the RFC 8032 vectors: valid, bit-flipped, S >= L, undecodable A,
+    small-order A and R; and the accumulator's limbs stay inside the lazy-carry bounds."""
     for pk, msg, sig in RFC8032:
         pk, msg, sig = bytes.fromhex(pk), bytes.fromhex(msg), bytes.fromhex(sig)
-        assert host.ed_verify_windowed_host(sig, pk, hashlib.sha512(sig[:32] + pk + msg).digest()) == 1
+        assert host.ed_verify_fast_host(sig, pk, hashlib.sha512(sig[:32] + pk + msg).digest()) == 1
+        bad = bytearray(sig); bad[5] ^= 2
+        assert host.ed_verify_fast_host(bytes(bad), pk, hashlib.sha512(bytes(bad[:32]) + pk + msg).digest()) == 0
     sks, pks, kidx, msg, sig, rng = make_sigs(400, 6, 7)
     order = sorted(range(400), key=lambda i: kidx[i])       # the harness caches the last key's table
     n_ok = 0
@@ -147,7 +230,7 @@ def test_windowed_core_equals_classic_core(host):
                 s[32:] = S.to_bytes(32, "little")
         s = bytes(s)
         k = hashlib.sha512(s[:32] + pk + m).digest()
-        a, b = host.ed_verify_core_host(s, pk, k), host.ed_verify_windowed_host(s, pk, k)
+        a, b = host.ed_verify_core_host(s, pk, k), host.ed_verify_fast_host(s, pk, k)
         assert a == b == int(openssl_ok(sks[kidx[i]], s, m)), i
         n_ok += a
     assert 150 < n_ok < 400
@@ -159,7 +242,12 @@ def test_windowed_core_equals_classic_core(host):
     for badpk in weird:
         for sg in (s0, bytes(32) + bytes(32), (1).to_bytes(32, "little") + bytes(32)):
             k = hashlib.sha512(sg[:32] + badpk + m0).digest()
-            assert host.ed_verify_core_host(sg, badpk, k) == host.ed_verify_windowed_host(sg, badpk, k), (badpk.hex(), sg.hex())
+            assert host.ed_verify_core_host(sg, badpk, k) == host.ed_verify_fast_host(sg, badpk, k), (badpk.hex(), sg.hex())
+    for i in range(6):
+        pk = pks[kidx[i]]
+        s = sig[i].tobytes()
+        m = host.ed_fast_limb_bound_host(s, pk, hashlib.sha512(s[:32] + pk + msg[i].tobytes()).digest())
+        assert 0 < m <= int(1.01 * 2 ** 25)
 
 
 @pytest.mark.gpu
@@ -192,3 +280,34 @@ def test_ed25519_gpu_batch(engine):
     sig2[7, 3] ^= 4
     got2 = engine.ed25519_verify_batch(np.frombuffer(b"".join(pks2), np.uint8).reshape(300, 32).copy(), kidx2, sig2, msg2)
     assert got2[7] == 1 and got2.sum() == 1
+    # the table cache: the same keys again (no build), the keys in another order with a duplicate and a NEW key (one build),
+    # a size that is not a multiple of the finish kernel's 512-item tiles, S >= L, and every signature invalid
+    builds0 = engine.stats()["launches"]
+    assert np.array_equal(engine.ed25519_verify_batch(pk_arr, kidx, sig, msg), expect)
+    assert engine.stats()["launches"] - builds0 == 2                   # accumulate + finish only
+    sks3, pks3, _, _, _, _ = make_sigs(1, 1, 99)
+    perm = [3, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]   # key 3 twice (positions 0 and 4)
+    pk_perm = np.concatenate([pk_arr[perm], np.frombuffer(pks3[0], np.uint8).reshape(1, 32)])
+    n2 = 5000
+    rep = np.resize(np.arange(n), n2)
+    k2 = kidx[rep].copy(); s2 = sig[rep].copy(); m2 = msg[rep].copy(); e2 = expect[rep].copy()
+    new_pos = {old: pos for pos, old in enumerate(perm) if pos != 0}    # old index -> a position of the same key
+    k2m = np.array([new_pos.get(int(k), 99) if k < 16 else 99 for k in k2], np.uint32)
+    k2m[::2] = np.where(k2[::2] == 3, 0, k2m[::2])                     # half of key 3's items through its other position
+    for i in range(40):                                                 # items under the new key: valid and corrupted
+        j = 100 + i
+        m2[j] = np.frombuffer(bytes(rng.randrange(256) for _ in range(32)), np.uint8)
+        s2[j] = np.frombuffer(sks3[0].sign(m2[j].tobytes()), np.uint8)
+        k2m[j] = 17
+        e2[j] = 0
+        if i % 4 == 0:
+            s2[j, 40] ^= 1
+            e2[j] = 1
+    Sbig = (int.from_bytes(s2[101, 32:].tobytes(), "little") + L).to_bytes(32, "little")
+    s2[101, 32:] = np.frombuffer(Sbig, np.uint8)                      # S + L: non-canonical
+    e2[101] = 1
+    got3 = engine.ed25519_verify_batch(pk_perm, k2m, s2, m2)
+    assert np.array_equal(got3, e2)
+    allbad = sig[:2304].copy(); allbad[:, 1] ^= 0x10
+    gotb = engine.ed25519_verify_batch(pk_arr, np.minimum(kidx[:2304], 14), allbad, msg[:2304])
+    assert (gotb == 1).all()

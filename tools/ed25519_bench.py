@@ -35,7 +35,7 @@ stream = torch.cuda.Stream(device=dev)
 
 
 def step():
-    _lib.check(eng._lib.bftq_ed25519_verify_batch_dev(eng._h, C.c_void_p(d[0].data_ptr()), K, C.c_void_p(d[1].data_ptr()), C.c_void_p(d[2].data_ptr()),
+    _lib.check(eng._lib.bftq_ed25519_verify_batch_dev(eng._h, pks.ctypes.data_as(C.c_void_p), K, C.c_void_p(d[1].data_ptr()), C.c_void_p(d[2].data_ptr()),
                                                       C.c_void_p(d[3].data_ptr()), N, C.c_void_p(st.data_ptr()), C.c_void_p(stream.cuda_stream)))
 
 
