@@ -183,9 +183,18 @@ struct EdCache {
   std::vector<cudaEvent_t> pending;              // builds that may still be running
 };
 
+// Large device scratch blocks kept across calls (bftq_read_responses_batch needs about 2.5 x the raw answers; a
+// cudaMalloc / cudaFree pair of a gigabyte per call costs milliseconds and serialises on the driver's allocator lock).
+struct ScratchCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;     // at most kKeep blocks
+  static constexpr size_t kKeep = 3;
+};
+
 struct bftq_engine {
   int device = 0;
   EdCache ed;
+  ScratchCache scratch;
   int sm_count = 0;
   std::mutex mu;
   std::vector<bftq::RsaKeyDev> h_keys;
@@ -220,6 +229,50 @@ struct bftq_engine {
 };
 
 namespace {
+
+// A device block of at least `bytes` (the smallest cached one that fits, else a fresh cudaMalloc).  The caller must have
+// finished every stream that touched the block before releasing it.
+void* scratch_acquire(bftq_engine* e, size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> g(e->scratch.mu);
+    int best = -1;
+    for (int i = 0; i < (int)e->scratch.free_list.size(); i++)
+      if (e->scratch.free_list[i].second >= bytes && (best < 0 || e->scratch.free_list[i].second < e->scratch.free_list[best].second)) best = i;
+    if (best >= 0) {
+      const auto b = e->scratch.free_list[best];
+      e->scratch.free_list.erase(e->scratch.free_list.begin() + best);
+      *got = b.second;
+      return b.first;
+    }
+  }
+  void* p = nullptr;
+  const size_t want = bytes + bytes / 8;                 // headroom: the next batch is rarely byte-identical in size
+  if (cudaMalloc(&p, want) == cudaSuccess) { *got = want; return p; }
+  cudaGetLastError();
+  {                                                      // out of memory: drop the cache and ask for the exact size
+    std::lock_guard<std::mutex> g(e->scratch.mu);
+    for (auto& b : e->scratch.free_list) cudaFree(b.first);
+    e->scratch.free_list.clear();
+  }
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *got = bytes;
+  return p;
+}
+void scratch_release(bftq_engine* e, void* p, size_t bytes) {
+  if (!p) return;
+  void* drop = nullptr;
+  {
+    std::lock_guard<std::mutex> g(e->scratch.mu);
+    e->scratch.free_list.emplace_back(p, bytes);
+    if (e->scratch.free_list.size() > ScratchCache::kKeep) {
+      int small = 0;
+      for (int i = 1; i < (int)e->scratch.free_list.size(); i++) if (e->scratch.free_list[i].second < e->scratch.free_list[small].second) small = i;
+      drop = e->scratch.free_list[small].first;
+      e->scratch.free_list.erase(e->scratch.free_list.begin() + small);
+    }
+  }
+  if (drop) cudaFree(drop);
+}
 
 void numa_probe(bftq_engine* e) {
   e->numa_valid = false;
@@ -626,6 +679,7 @@ void bftq_shutdown(bftq_engine* e) {
   if (e->d_keys) cudaFree(e->d_keys);
   if (e->d_keys32) cudaFree(e->d_keys32);
   cudaDeviceSynchronize();
+  for (auto& b : e->scratch.free_list) cudaFree(b.first);
   for (cudaEvent_t ev : e->ed.pending) cudaEventDestroy(ev);
   if (e->ed.d_tab) cudaFree(e->ed.d_tab);
   if (e->ed.d_hdr) cudaFree(e->ed.d_hdr);
@@ -821,7 +875,7 @@ namespace {
 // found by the 32 key bytes.  Slots are immutable once built and never move, so kernels of any stream may read them;
 // a slot built on one stream is ordered before readers on other streams by the build's event.  The cache is bounded
 // (BFTQ_ED25519_CACHE_SLOTS, default 256 = 128 MB): a batch whose new keys do not fit runs the table-free kernel.
-int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, cudaStream_t st, std::vector<uint32_t>& slot_of_key, bool& fits) {
+int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, uint64_t max_new, cudaStream_t st, std::vector<uint32_t>& slot_of_key, bool& fits) {
   EdCache& c = e->ed;
   fits = false;
   if (c.cap_slots == 0) {
@@ -831,7 +885,9 @@ int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, cu
     void* tab = nullptr; void* hdr = nullptr;
     if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return BFTQ_OK; }          // no room: table-free kernel
     if (cudaMalloc(&hdr, (size_t)cap * sizeof(bftq::EdSlotHdr)) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); return BFTQ_OK; }
-    CU(cudaMemset(hdr, 0, (size_t)cap * sizeof(bftq::EdSlotHdr)));
+    // on the call's stream: a legacy-stream cudaMemset is NOT ordered against the non-blocking streams the builds run on
+    // (it raced with the first build's header writes and wiped the 'key decodes' flags: every signature of the first batch invalid)
+    if (cudaMemsetAsync(hdr, 0, (size_t)cap * sizeof(bftq::EdSlotHdr), st) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); cudaFree(hdr); return fail(BFTQ_ERR_CUDA, "cudaMemsetAsync failed"); }
     c.d_tab = (bftq::ed::gea*)tab; c.d_hdr = (bftq::EdSlotHdr*)hdr; c.cap_slots = cap; c.used = 0;
   }
   // which keys are new?
@@ -849,6 +905,7 @@ int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, cu
   }
   const uint32_t first = need_base ? 0u : c.used;
   const uint32_t n_new = (uint32_t)fresh.size() + (need_base ? 1u : 0u);
+  if (fresh.size() > max_new) return BFTQ_OK;                  // too few signatures to pay for this many new tables
   if ((uint64_t)first + n_new > c.cap_slots) return BFTQ_OK;   // does not fit: caller takes the table-free kernel
   // earlier builds on other streams must be complete before this stream reads their slots
   for (size_t i = 0; i < c.pending.size();) {
@@ -890,17 +947,18 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32
   if (n_items == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  // Signatures that share keys (OpenPGP: a handful of keys, many signatures) run against the cached window tables: at most
-  // 64 mixed additions per signature and no doubling.  With few signatures per key (a table costs about 400
-  // verifications' worth of work, once per key and engine) the table-free double-and-add kernel is used.
+  // Signatures run against the cached window tables: at most 64 mixed additions each and no doubling.  A table costs
+  // about 400 such verifications' worth of work once per key and engine (about 50 table-free ones), so a batch may
+  // bring one NEW key per 32 signatures; keys that are cached already cost nothing, whatever the batch size.  Batches
+  // with more new keys than that (every signature under its own key, say) take the table-free double-and-add kernel.
   static const bool no_tables = [] { const char* v = getenv("BFTQ_ED25519_TABLES"); return v && atoi(v) == 0; }();
-  bool tables = !no_tables && n_keys > 0 && n_keys <= 4096 && n_items >= 128ull * ((uint64_t)n_keys + 1);
+  bool tables = !no_tables && n_keys > 0 && n_keys <= 4096;
   int launches = 0;
   if (tables) {
     std::vector<uint32_t> slot_of_key;
     std::lock_guard<std::mutex> g(e->ed.mu);                   // held while this call's work is enqueued
     const uint64_t before = e->ed.builds;
-    const int rc = ed_cache_prepare(e, pubkeys, n_keys, st, slot_of_key, tables);
+    const int rc = ed_cache_prepare(e, pubkeys, n_keys, n_items / 32, st, slot_of_key, tables);
     if (rc) return rc;
     if (tables) {
       launches += e->ed.builds != before ? 2 : 0;

@@ -121,7 +121,7 @@ __device__ __forceinline__ void mont_sqr(uint32_t (&out)[16], const uint32_t (&a
   for (int k = 0; k < W + 2; k++) A.O[k] = 0u;
   uint32_t cin = 0u, Z = 0u;
 #ifndef BFTQ_SQR_UNROLL
-#define BFTQ_SQR_UNROLL 1
+#define BFTQ_SQR_UNROLL 2
 #endif
   constexpr int kSqrUnroll = BFTQ_SQR_UNROLL;      // owner steps per loop body (code size x this)
 #pragma unroll kSqrUnroll

@@ -321,6 +321,13 @@ struct RsaKey32 {               // per key, radix 2^32 little-endian words
 #ifndef BFTQ_K1_SYNC
 #define BFTQ_K1_SYNC 2
 #endif
+// 1 = the exponentiation runs as one loop over a four-op program (one squaring and one product instance in the kernel:
+// 66 KB of SASS instead of 116 KB).  Measured with BFTQ_K1_SYNC 2 (profiles/k1_variants_r02c.txt, two streams, 65 536 items):
+// straight-line 58.1 M verifies/s, unified 58.7, unified + two owner steps of the squaring per loop body
+// (BFTQ_SQR_UNROLL 2, the default now) 60.6, + BFTQ_MUL_UNROLL 2 60.8 (not taken: code size for 0.2 %).
+#ifndef BFTQ_K1_UNIFIED
+#define BFTQ_K1_UNIFIED 1
+#endif
 // SQ: the squarings of the exponentiation go through mont_sqr (rsa_square_r32.cuh) instead of mont_mul(y, y).
 template <int BLOCK, int MIN_BLOCKS, bool SQ>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
@@ -365,17 +372,9 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
     const uint32_t e = __ldg(&key->e);
     const uint8_t* sp = sig + item * (uint64_t)kRsaBytes;
     bool s_ge_n;
-    {
-      uint32_t xs[W], r2[W];
 #pragma unroll
-      for (int j = 0; j < W; j++) xs[j] = be_word(sp, r * W + j);
-      s_ge_n = group_ge(xs, nd, gbase);
-#pragma unroll
-      for (int j = 0; j < W; j++) r2[j] = __ldg(&key->r2[r * W + j]);
-      mont_mul(y, xs, r2, nd, n0inv, r, gbase);           // s * R mod n (almost reduced)
-    }
-#pragma unroll
-    for (int j = 0; j < W; j++) xm_s[j][threadIdx.x] = y[j];
+    for (int j = 0; j < W; j++) y[j] = be_word(sp, r * W + j);
+    s_ge_n = group_ge(y, nd, gbase);
     const int nb = 32 - __clz(e);
     int nbmax = nb;
 #pragma unroll
@@ -387,6 +386,64 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
       __syncthreads();
       nbmax = nbmax_s;
     }
+#if BFTQ_K1_UNIFIED
+    // The whole exponentiation as ONE loop over a small program, so that the kernel holds a single instance of the
+    // squaring and a single instance of the general product (the straight-line form below has two and three: 75 KB of
+    // hot code per task instead of 31 KB; the instruction caches hold 32 KB).
+    //   op 0: y = s * R^2 (to Montgomery form; also parked as xm)      op 1: the squaring of `bit`
+    //   op 2: y *= xm after the squaring of an interior 1 bit            op 3: the last product, by the PLAIN s (or 1)
+    int op = 0, bit = nbmax - 2;
+#pragma unroll 1
+    for (;;) {
+      if (op == 1) {
+        if (SQ) mont_sqr<kStepSync>(t, y, nd, n0inv, r, gbase); else mont_mul<W, kStepSync>(t, y, y, nd, n0inv, r, gbase);
+        if (BFTQ_K1_SYNC >= 2) __syncthreads();              // every warp of the block runs nbmax - 1 squarings
+        if (bit <= nb - 2) {
+#pragma unroll
+          for (int j = 0; j < W; j++) y[j] = t[j];
+        }
+        const bool mul = bit >= 1 && bit <= nb - 2 && ((e >> bit) & 1u);
+        if (__any_sync(kFull, mul)) op = 2;
+        else { bit--; op = bit >= 0 ? 1 : 3; }
+      } else {
+        uint32_t bop[W];
+        if (op == 0) {
+#pragma unroll
+          for (int j = 0; j < W; j++) bop[j] = __ldg(&key->r2[r * W + j]);
+        } else if (op == 2) {
+#pragma unroll
+          for (int j = 0; j < W; j++) bop[j] = xm_s[j][threadIdx.x];
+        } else {                                              // plain s (bit 0 set) or plain 1: leaves Montgomery form
+#pragma unroll
+          for (int j = 0; j < W; j++) bop[j] = ((e & 1u) && nb >= 2) ? be_word(sp, r * W + j) : ((r == 0 && j == 0) ? 1u : 0u);
+        }
+        mont_mul(t, y, bop, nd, n0inv, r, gbase);
+        if (op == 3) break;
+        if (op == 0) {
+#pragma unroll
+          for (int j = 0; j < W; j++) { y[j] = t[j]; xm_s[j][threadIdx.x] = t[j]; }
+          op = bit >= 0 ? 1 : 3;
+        } else {
+          if (bit <= nb - 2 && ((e >> bit) & 1u)) {
+#pragma unroll
+            for (int j = 0; j < W; j++) y[j] = t[j];
+          }
+          bit--;
+          op = bit >= 0 ? 1 : 3;
+        }
+      }
+    }
+#else
+    {
+      uint32_t r2[W];
+#pragma unroll
+      for (int j = 0; j < W; j++) r2[j] = __ldg(&key->r2[r * W + j]);
+      mont_mul(t, y, r2, nd, n0inv, r, gbase);              // s * R mod n (almost reduced)
+#pragma unroll
+      for (int j = 0; j < W; j++) y[j] = t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < W; j++) xm_s[j][threadIdx.x] = y[j];
 #pragma unroll 1
     for (int bit = nbmax - 2; bit >= 1; bit--) {
       const bool active = bit <= nb - 2;
@@ -421,6 +478,7 @@ rsa_verify_r32_kernel(const RsaKey32* __restrict__ keys, const uint32_t nkeys, c
       for (int j = 0; j < W; j++) m1[j] = ((e & 1u) && nb >= 2) ? be_word(sp, r * W + j) : ((r == 0 && j == 0) ? 1u : 0u);
       mont_mul(t, y, m1, nd, n0inv, r, gbase);            // plain operand: leaves Montgomery form
     }
+#endif
     cond_sub(t, nd, r, gbase);                            // t < 2^2048 < 2n  ->  t mod n
 
     const uint8_t* dp = digest + item * (uint64_t)dlen;

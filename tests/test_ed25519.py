@@ -270,9 +270,9 @@ def test_ed25519_gpu_batch(engine):
     got = engine.ed25519_verify_batch(pk_arr, kidx, sig, msg)          # 4096 signatures, 16 keys: the window-table kernel
     assert np.array_equal(got, expect)
     assert (got == 0).sum() > 2500 and (got == 1).sum() > 1000
-    for size in (1, 2, 31, 129):                                        # few signatures per key: the double-and-add kernel
+    for size in (1, 2, 31, 129):                                        # tiny batches under keys that are cached by now
         assert np.array_equal(engine.ed25519_verify_batch(pk_arr, kidx[:size].copy(), sig[:size].copy(), msg[:size].copy()), expect[:size])
-    # every signature under its own key (no sharing): classic kernel at size
+    # every signature under its own new key (no sharing): the table-free double-and-add kernel
     sks2, pks2, kidx2, msg2, sig2, _ = make_sigs(300, 300, 5)
     kidx2 = np.arange(300, dtype=np.uint32)
     for i in range(300):
@@ -280,6 +280,9 @@ def test_ed25519_gpu_batch(engine):
     sig2[7, 3] ^= 4
     got2 = engine.ed25519_verify_batch(np.frombuffer(b"".join(pks2), np.uint8).reshape(300, 32).copy(), kidx2, sig2, msg2)
     assert got2[7] == 1 and got2.sum() == 1
+    pk2 = np.frombuffer(b"".join(pks2), np.uint8).reshape(300, 32).copy()
+    got2b = engine.ed25519_verify_batch(pk2[5:12], np.arange(7, dtype=np.uint32), sig2[5:12].copy(), msg2[5:12].copy())   # 7 signatures, 7 new keys
+    assert got2b.tolist() == [0, 0, 1, 0, 0, 0, 0]
     # the table cache: the same keys again (no build), the keys in another order with a duplicate and a NEW key (one build),
     # a size that is not a multiple of the finish kernel's 512-item tiles, S >= L, and every signature invalid
     builds0 = engine.stats()["launches"]
@@ -308,6 +311,8 @@ def test_ed25519_gpu_batch(engine):
     e2[101] = 1
     got3 = engine.ed25519_verify_batch(pk_perm, k2m, s2, m2)
     assert np.array_equal(got3, e2)
-    allbad = sig[:2304].copy(); allbad[:, 1] ^= 0x10
-    gotb = engine.ed25519_verify_batch(pk_arr, np.minimum(kidx[:2304], 14), allbad, msg[:2304])
-    assert (gotb == 1).all()
+    allbad = sig[:2304].copy(); allbad[:, 1] ^= 0x10                   # R damaged everywhere (two earlier flips are undone by it)
+    kb = np.minimum(kidx[:2304], 14)
+    expb = np.array([0 if openssl_ok(sks[kb[i]], allbad[i].tobytes(), msg[i].tobytes()) else 1 for i in range(2304)], np.uint8)
+    gotb = engine.ed25519_verify_batch(pk_arr, kb, allbad, msg[:2304])
+    assert np.array_equal(gotb, expb) and (gotb == 1).sum() > 2290
