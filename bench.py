@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 MACS_PER_VERIFY = 156864          # 19 Montgomery products x (2*64^2 + 64) word-MACs, SURVEY §8(d)
 EXECUTED_MACS_PER_VERIFY = 2 * 8192 + 16 * (4096 + 2176)     # 2 general products + 16 squarings (544 a x a + 1024 n x q IMAD.WIDE per lane)
-NCU_DRAM_BYTES_PER_LAUNCH = 19271424      # profiles/ncu_rsa_verify_r02a_sq.txt: 19.271424 MB read + 0 B written per 65536-item launch
+NCU_DRAM_BYTES_PER_LAUNCH = 19225600      # profiles/ncu_rsa_verify_r02c_unified.txt: 19.2256 MB read + 0 B written per 65536-item launch
 BYTES_PER_VERIFY = 549            # n 256 + s 256 + digest 32 + key idx 4 + status 1, SURVEY §8(d)
 ITEMS = 65536
 NKEYS = 16
@@ -700,7 +700,7 @@ def run_gpu(args, rank, local_rank, world):
         "config": {"workload": WORKLOAD,
                    "per_gpu_batch": ITEMS, "l2": "inputs rotated over %d distinct device copies (%d MB > 126 MB L2)"
                    % (copies, copies * ITEMS * 292 // 2 ** 20), "lanes_per_signature": int(os.environ.get("BFTQ_RSA_T", "4")), "streams_in_flight": NSTREAMS,
-                   "kernel": os.environ.get("BFTQ_RSA_KERNEL", "r32sq (default: radix 2^32, dedicated squaring)"),
+                   "kernel": os.environ.get("BFTQ_RSA_KERNEL", "r32sq (default: radix 2^32, dedicated squaring, unified exponent loop, in-block barrier per product)"),
                    "numa_node": numa_node, "host_cores_per_rank": cores_rank},
         "gpu_launches": int(gpu_launches),
         "sustained": {"value": ITEMS * world / (sus_ms_step * 1e-3), "unit": "verifies/s", "launches": n_sus, "seconds": sus_ms * 1e-3,
@@ -767,7 +767,7 @@ def run_gpu(args, rank, local_rank, world):
         "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s (32x32+64 IMAD.WIDE on the FMA-heavy pipe)",
                      "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one rsa_verify_r32_kernel launch (65536 items) in "
-                                       "profiles/ncu_rsa_verify_r02a_sq.txt (ncu --set full); algorithmic bytes per launch = %d" % (BYTES_PER_VERIFY * ITEMS),
+                                       "profiles/ncu_rsa_verify_r02c_unified.txt (ncu --set full); algorithmic bytes per launch = %d" % (BYTES_PER_VERIFY * ITEMS),
                      "peak_source": "measured live on this GPU: dependency-free fused IMAD.WIDE.U32 stream, 64 warps/SM (bftq_measure_int_peak)",
                      "kernel": "rsa_verify_r32_kernel<128, 4, SQ>", "kernel_ms_avg": k_avg_ms, "kernel_ms_alone": serial_ms[len(serial_ms) // 2],
                      "kernel_ms_note": "avg = timed region / launches (launches alternate over %d streams); alone = median of the serial warm-up launches" % NSTREAMS,
@@ -796,8 +796,8 @@ def run_gpu(args, rank, local_rank, world):
         out["roofline_secondary"]["k3_lagrange"] = {
             "bound": "hbm", "achieved": k3_bytes / (ed["k3_kernel_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": k3_bytes / (ed["k3_kernel_ms"] * 1e-3) / 1e9 / hbm_peak, "kernel_ms": ed["k3_kernel_ms"], "bytes_per_launch": k3_bytes,
-            "note": "lagrange_combine_kernel<8> on %d combines of 10 shares mod the P-256 order: 393 B per combine (SURVEY §8d); ten Fermat inversions per "
-                    "combine make it compute-bound in practice" % ed["k3_items"]}
+            "note": "lagrange_combine_kernel<8> on %d combines of 10 shares mod the P-256 order: 393 B per combine (SURVEY §8d); one thread per "
+                    "combine (small-integer inversions + about 80 Montgomery products), under one wave: latency-bound, HBM idle" % ed["k3_items"]}
     if world == 1:
         from oracle import c_oracle
         threads = host_cores()

@@ -363,46 +363,3 @@ BFTQ_HD bool verify_core(const uint8_t* sig, const uint8_t* pk, const uint32_t (
 
 
 }}  // namespace bftq::ed
-
-#ifdef __CUDACC__
-#include "pgp_digest.cuh"
-namespace bftq {
-// One thread per signature.  status: 0 valid, 1 invalid, 4 key index out of range.
-__global__ void __launch_bounds__(128)
-ed25519_verify_kernel(const uint8_t* __restrict__ pubkeys, const uint32_t n_keys, const uint32_t* __restrict__ key_idx,
-                      const uint8_t* __restrict__ sig, const uint8_t* __restrict__ msg, const uint64_t n_items,
-                      uint8_t* __restrict__ status) {
-  const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= n_items) return;
-  const uint32_t kidx = __ldg(key_idx + item);
-  if (kidx >= n_keys) { status[item] = 4; return; }
-  uint8_t s[64], a[32];
-  for (int i = 0; i < 64; i++) s[i] = __ldg(sig + item * 64 + i);
-  for (int i = 0; i < 32; i++) a[i] = __ldg(pubkeys + (uint64_t)kidx * 32 + i);
-  // k = SHA-512(R || A || M): 96 bytes = one padded block
-  uint64_t w[16];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    uint64_t r = 0, aa = 0, m = 0;
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-      r = (r << 8) | s[8 * i + b];
-      aa = (aa << 8) | a[8 * i + b];
-      m = (m << 8) | (uint64_t)__ldg(msg + item * 32 + 8 * i + b);
-    }
-    w[i] = r; w[4 + i] = aa; w[8 + i] = m;
-  }
-  w[12] = 0x8000000000000000ull; w[13] = 0; w[14] = 0;
-  w[15] = 96 * 8;
-  uint64_t h[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
-                   0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
-  sha512_compress(h, w);
-  uint8_t dg[64];
-  for (int i = 0; i < 8; i++) for (int b = 0; b < 8; b++) dg[8 * i + b] = (uint8_t)(h[i] >> (56 - 8 * b));
-  uint32_t k[8];
-  ed::sc_reduce64(k, dg);
-  status[item] = ed::verify_core(s, a, k) ? 0 : 1;
-}
-
-}  // namespace bftq
-#endif

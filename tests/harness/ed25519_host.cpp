@@ -11,6 +11,11 @@ int ed_verify_core_host(const uint8_t* sig, const uint8_t* pk, const uint8_t* k6
   sc_reduce64(k, k64);
   return verify_core(sig, pk, k) ? 1 : 0;
 }
+int ed_verify_core_fast_host(const uint8_t* sig, const uint8_t* pk, const uint8_t* k64) {
+  uint32_t k[8];
+  sc_reduce64(k, k64);
+  return verify_core_fast(sig, pk, k) ? 1 : 0;
+}
 void ed_fe_mul_host(const uint8_t* a, const uint8_t* b, uint8_t* out) { fe x, y, z; fe_frombytes(x, a); fe_frombytes(y, b); fe_mul(z, x, y); fe_tobytes(out, z); }
 void ed_fe_invert_host(const uint8_t* a, uint8_t* out) { fe x, z; fe_frombytes(x, a); fe_invert(z, x); fe_tobytes(out, z); }
 void ed_fe_addsubmul_host(const uint8_t* a, const uint8_t* b, uint8_t* out) {   // (a+b)*(a-b) exercises uncarried inputs

@@ -214,8 +214,10 @@ def test_fast_core_equals_classic_core(host):
     for pk, msg, sig in RFC8032:
         pk, msg, sig = bytes.fromhex(pk), bytes.fromhex(msg), bytes.fromhex(sig)
         assert host.ed_verify_fast_host(sig, pk, hashlib.sha512(sig[:32] + pk + msg).digest()) == 1
+        assert host.ed_verify_core_fast_host(sig, pk, hashlib.sha512(sig[:32] + pk + msg).digest()) == 1
         bad = bytearray(sig); bad[5] ^= 2
         assert host.ed_verify_fast_host(bytes(bad), pk, hashlib.sha512(bytes(bad[:32]) + pk + msg).digest()) == 0
+        assert host.ed_verify_core_fast_host(bytes(bad), pk, hashlib.sha512(bytes(bad[:32]) + pk + msg).digest()) == 0
     sks, pks, kidx, msg, sig, rng = make_sigs(400, 6, 7)
     order = sorted(range(400), key=lambda i: kidx[i])       # the harness caches the last key's table
     n_ok = 0
@@ -230,8 +232,8 @@ def test_fast_core_equals_classic_core(host):
                 s[32:] = S.to_bytes(32, "little")
         s = bytes(s)
         k = hashlib.sha512(s[:32] + pk + m).digest()
-        a, b = host.ed_verify_core_host(s, pk, k), host.ed_verify_fast_host(s, pk, k)
-        assert a == b == int(openssl_ok(sks[kidx[i]], s, m)), i
+        a, b, c = host.ed_verify_core_host(s, pk, k), host.ed_verify_fast_host(s, pk, k), host.ed_verify_core_fast_host(s, pk, k)
+        assert a == b == c == int(openssl_ok(sks[kidx[i]], s, m)), i
         n_ok += a
     assert 150 < n_ok < 400
     s0, m0 = sig[0].tobytes(), msg[0].tobytes()
@@ -242,7 +244,7 @@ def test_fast_core_equals_classic_core(host):
     for badpk in weird:
         for sg in (s0, bytes(32) + bytes(32), (1).to_bytes(32, "little") + bytes(32)):
             k = hashlib.sha512(sg[:32] + badpk + m0).digest()
-            assert host.ed_verify_core_host(sg, badpk, k) == host.ed_verify_fast_host(sg, badpk, k), (badpk.hex(), sg.hex())
+            assert host.ed_verify_core_host(sg, badpk, k) == host.ed_verify_fast_host(sg, badpk, k) == host.ed_verify_core_fast_host(sg, badpk, k), (badpk.hex(), sg.hex())
     for i in range(6):
         pk = pks[kidx[i]]
         s = sig[i].tobytes()
