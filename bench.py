@@ -44,9 +44,10 @@ ITEMS = 65536
 NKEYS = 16
 WORKLOAD = ("batch 65536 RSA-2048 PGP signature verifies (BASELINE configs[1]), 16 keys, e=65537, SHA-256, "
             "1% corrupted + 0.1% unknown signer")
-# K1b (ed25519_fast.cuh): expected 63.75 non-zero signed radix-256 digits x 7 field products (100 IMAD.WIDE each) per mixed addition
-# + 126 word products of the Barrett reduction + kernel 2: 5 products per signature + 1/8 of an inversion (254 squarings x 55 + 11 x 100)
-ED25519_MACS = int(63.75 * 700 + 126 + 500 + (254 * 55 + 11 * 100) / 8)        # = 47 134 executed 32x32->64 multiplies per verification
+# K1b (ed25519_fast.cuh): expected 21.4 + 26.0 non-zero signed digits (radix 2^12 for S / the base point, 2^10 for k / the key) x 7 field
+# products (100 IMAD.WIDE each) per mixed addition + 126 word products of the Barrett reduction + kernel 2: 5 products per signature + 1/8 of
+# an inversion (254 squarings x 55 + 11 x 100)
+ED25519_MACS = int(47.4 * 700 + 126 + 500 + (254 * 55 + 11 * 100) / 8)        # = 35 689 executed 32x32->64 multiplies per verification
 
 
 def host_cores():
@@ -789,7 +790,7 @@ def run_gpu(args, rank, local_rank, world):
         out["roofline_secondary"]["k1b_ed25519"] = {
             "bound": "int_alu", "achieved": ED25519_MACS * ed["value"] / 1e12, "peak": int_peak / 1e12, "unit": "Tmac/s",
             "frac": ED25519_MACS * ed["value"] / int_peak, "executed_macs_per_verify": ED25519_MACS,
-            "note": "cached radix-256 window tables: expected 63.75 mixed additions x 7 field products x 100 IMAD.WIDE + Barrett reduction (126) in "
+            "note": "cached window tables (radix 2^12 base point, radix 2^10 keys): expected 47.4 mixed additions x 7 field products x 100 IMAD.WIDE + Barrett reduction (126) in "
                     "ed25519_accumulate_kernel, 5 products + 1/8 inversion per signature in ed25519_finish_kernel; SHA-512 and the 19*g / 2*f "
                     "pre-scalings (plain IMAD) not counted; the first K1b executed 134 970 per verification"}
         k3_bytes = ed["k3_items"] * (10 * (4 + 32) + 32 + 1)

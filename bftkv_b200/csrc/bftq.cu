@@ -175,7 +175,8 @@ struct PackerPool {
 // Ed25519 window-table cache (see ed_cache_prepare).
 struct EdCache {
   std::mutex mu;
-  bftq::ed::gea* d_tab = nullptr;                // cap_slots x 4096 entries of 128 bytes
+  bftq::ed::gea* d_tab = nullptr;                // cap_slots x FxA::entries entries of 128 bytes (keys)
+  bftq::ed::gea* d_tabB = nullptr;               // FxB::entries entries (the base point)
   bftq::EdSlotHdr* d_hdr = nullptr;
   uint32_t cap_slots = 0, used = 0;
   uint64_t builds = 0;                           // slots built so far
@@ -682,6 +683,7 @@ void bftq_shutdown(bftq_engine* e) {
   for (auto& b : e->scratch.free_list) cudaFree(b.first);
   for (cudaEvent_t ev : e->ed.pending) cudaEventDestroy(ev);
   if (e->ed.d_tab) cudaFree(e->ed.d_tab);
+  if (e->ed.d_tabB) cudaFree(e->ed.d_tabB);
   if (e->ed.d_hdr) cudaFree(e->ed.d_hdr);
   for (void* p : e->retired) cudaFree(p);
   delete e;
@@ -871,30 +873,38 @@ int bftq_rsa_verify_batch_k(bftq_engine* e, uint32_t key_bytes, const uint32_t* 
 
 // ---- K1b --------------------------------------------------------------------------------------
 namespace {
-// Per-engine cache of Ed25519 window tables (ed25519_fast.cuh): slot 0 = the base point, slot s > 0 = -A of one key,
-// found by the 32 key bytes.  Slots are immutable once built and never move, so kernels of any stream may read them;
-// a slot built on one stream is ordered before readers on other streams by the build's event.  The cache is bounded
-// (BFTQ_ED25519_CACHE_SLOTS, default 256 = 128 MB): a batch whose new keys do not fit runs the table-free kernel.
+// Per-engine cache of Ed25519 window tables (ed25519_fast.cuh): ONE radix-2^12 table of the base point (5.8 MB, built with the
+// cache) and one radix-2^10 table of -A per key (1.7 MB per slot), found by the 32 key bytes.  Slots are immutable once built
+// and never move, so kernels of any stream may read them; a table built on one stream is ordered before readers on other
+// streams by the build's event.  The cache is bounded (BFTQ_ED25519_CACHE_SLOTS, default 256 = 436 MB): a batch whose new
+// keys do not fit runs the table-free kernel.
+int ed_build_tables(EdCache& c, cudaStream_t st, uint32_t first_slot, uint32_t n_points, bool base_point) {
+  namespace ed = bftq::ed;
+  const int nw = base_point ? ed::FxB::windows : ed::FxA::windows, wbits = base_point ? ed::kFxWB : ed::kFxWA;
+  const int multiples = base_point ? ed::FxB::multiples : ed::FxA::multiples;
+  ed::gex* d_bases = nullptr;
+  CU(cudaMallocAsync((void**)&d_bases, (size_t)n_points * nw * sizeof(ed::gex), st));
+  bftq::ed25519_bases_kernel<<<(n_points + 31) / 32, 32, 0, st>>>(c.d_hdr, first_slot, n_points, d_bases, nw, wbits, base_point ? 1 : 0);
+  const uint64_t threads = (uint64_t)n_points * nw * (multiples / ed::kFxChunk);
+  ed::gea* dst = base_point ? c.d_tabB : c.d_tab + (size_t)first_slot * ed::FxA::entries;
+  bftq::ed25519_multiples_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_bases, n_points, nw, multiples, dst);
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_bases, st));
+  cudaEvent_t ev;
+  CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, st));
+  c.pending.push_back(ev);
+  return BFTQ_OK;
+}
+
 int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, uint64_t max_new, cudaStream_t st, std::vector<uint32_t>& slot_of_key, bool& fits) {
+  namespace ed = bftq::ed;
   EdCache& c = e->ed;
   fits = false;
-  if (c.cap_slots == 0) {
-    uint32_t cap = 256;
-    if (const char* v = getenv("BFTQ_ED25519_CACHE_SLOTS")) cap = (uint32_t)std::max(2, atoi(v));
-    const size_t bytes = (size_t)cap * bftq::ed::kFxEntries * sizeof(bftq::ed::gea);
-    void* tab = nullptr; void* hdr = nullptr;
-    if (cudaMalloc(&tab, bytes) != cudaSuccess) { cudaGetLastError(); return BFTQ_OK; }          // no room: table-free kernel
-    if (cudaMalloc(&hdr, (size_t)cap * sizeof(bftq::EdSlotHdr)) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); return BFTQ_OK; }
-    // on the call's stream: a legacy-stream cudaMemset is NOT ordered against the non-blocking streams the builds run on
-    // (it raced with the first build's header writes and wiped the 'key decodes' flags: every signature of the first batch invalid)
-    if (cudaMemsetAsync(hdr, 0, (size_t)cap * sizeof(bftq::EdSlotHdr), st) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); cudaFree(hdr); return fail(BFTQ_ERR_CUDA, "cudaMemsetAsync failed"); }
-    c.d_tab = (bftq::ed::gea*)tab; c.d_hdr = (bftq::EdSlotHdr*)hdr; c.cap_slots = cap; c.used = 0;
-  }
   // which keys are new?
   std::vector<std::string> fresh;
   std::map<std::string, uint32_t> fresh_idx;
   slot_of_key.assign(n_keys, 0);
-  const bool need_base = c.used == 0;
   for (uint32_t i = 0; i < n_keys; i++) {
     std::string kb((const char*)pubkeys + (size_t)i * 32, 32);
     auto it = c.slot_of.find(kb);
@@ -903,34 +913,42 @@ int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, ui
     if (f == fresh_idx.end()) { f = fresh_idx.emplace(kb, (uint32_t)fresh.size()).first; fresh.push_back(kb); }
     slot_of_key[i] = 0x80000000u | f->second;                 // resolved below
   }
-  const uint32_t first = need_base ? 0u : c.used;
-  const uint32_t n_new = (uint32_t)fresh.size() + (need_base ? 1u : 0u);
   if (fresh.size() > max_new) return BFTQ_OK;                  // too few signatures to pay for this many new tables
+  if (c.cap_slots == 0) {                                      // first use: the cache itself and the base point's table
+    uint32_t cap = 256;
+    if (const char* v = getenv("BFTQ_ED25519_CACHE_SLOTS")) cap = (uint32_t)std::max(1, atoi(v));
+    void *tab = nullptr, *tabB = nullptr, *hdr = nullptr;
+    if (cudaMalloc(&tab, (size_t)cap * ed::FxA::entries * sizeof(ed::gea)) != cudaSuccess ||
+        cudaMalloc(&tabB, (size_t)ed::FxB::entries * sizeof(ed::gea)) != cudaSuccess ||
+        cudaMalloc(&hdr, (size_t)cap * sizeof(bftq::EdSlotHdr)) != cudaSuccess) {
+      cudaGetLastError();                                      // no room: table-free kernel
+      if (tab) cudaFree(tab);
+      if (tabB) cudaFree(tabB);
+      return BFTQ_OK;
+    }
+    // on the call's stream: a legacy-stream cudaMemset is NOT ordered against the non-blocking streams the builds run on
+    // (it raced with the first build's header writes and wiped the 'key decodes' flags: every signature of the first batch invalid)
+    if (cudaMemsetAsync(hdr, 0, (size_t)cap * sizeof(bftq::EdSlotHdr), st) != cudaSuccess) { cudaGetLastError(); cudaFree(tab); cudaFree(tabB); cudaFree(hdr); return fail(BFTQ_ERR_CUDA, "cudaMemsetAsync failed"); }
+    c.d_tab = (ed::gea*)tab; c.d_tabB = (ed::gea*)tabB; c.d_hdr = (bftq::EdSlotHdr*)hdr; c.cap_slots = cap; c.used = 0;
+    const int rc = ed_build_tables(c, st, 0, 1, true);
+    if (rc) return rc;
+    c.builds += 1;
+  }
+  const uint32_t first = c.used;
+  const uint32_t n_new = (uint32_t)fresh.size();
   if ((uint64_t)first + n_new > c.cap_slots) return BFTQ_OK;   // does not fit: caller takes the table-free kernel
-  // earlier builds on other streams must be complete before this stream reads their slots
+  // earlier builds on other streams must be complete before this stream reads their tables
   for (size_t i = 0; i < c.pending.size();) {
     if (cudaEventQuery(c.pending[i]) == cudaSuccess) { cudaEventDestroy(c.pending[i]); c.pending[i] = c.pending.back(); c.pending.pop_back(); }
     else { cudaGetLastError(); CU(cudaStreamWaitEvent(st, c.pending[i], 0)); i++; }
   }
   if (n_new) {
-    const uint32_t key_slot0 = first + (need_base ? 1u : 0u);
-    if (!fresh.empty()) {
-      std::vector<bftq::EdSlotHdr> h(fresh.size());
-      for (size_t i = 0; i < fresh.size(); i++) { memset(&h[i], 0, sizeof(h[i])); memcpy(h[i].key, fresh[i].data(), 32); }
-      CU(cudaMemcpyAsync(c.d_hdr + key_slot0, h.data(), h.size() * sizeof(bftq::EdSlotHdr), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
-    }
-    bftq::ed::gex* d_bases = nullptr;
-    CU(cudaMallocAsync((void**)&d_bases, (size_t)n_new * bftq::ed::kFxWindows * sizeof(bftq::ed::gex), st));
-    bftq::ed25519_bases_kernel<<<(n_new + 31) / 32, 32, 0, st>>>(c.d_hdr, first, n_new, d_bases);
-    const uint64_t threads = (uint64_t)n_new * bftq::ed::kFxWindows * (bftq::ed::kFxMultiples / bftq::ed::kFxChunk);
-    bftq::ed25519_multiples_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(d_bases, first, n_new, c.d_tab);
-    CU(cudaGetLastError());
-    CU(cudaFreeAsync(d_bases, st));
-    cudaEvent_t ev;
-    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, st));
-    c.pending.push_back(ev);
-    for (size_t i = 0; i < fresh.size(); i++) c.slot_of.emplace(fresh[i], key_slot0 + (uint32_t)i);
+    std::vector<bftq::EdSlotHdr> h(fresh.size());
+    for (size_t i = 0; i < fresh.size(); i++) { memset(&h[i], 0, sizeof(h[i])); memcpy(h[i].key, fresh[i].data(), 32); }
+    CU(cudaMemcpyAsync(c.d_hdr + first, h.data(), h.size() * sizeof(bftq::EdSlotHdr), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    const int rc = ed_build_tables(c, st, first, n_new, false);
+    if (rc) return rc;
+    for (size_t i = 0; i < fresh.size(); i++) c.slot_of.emplace(fresh[i], first + (uint32_t)i);
     c.used = first + n_new;
     c.builds += n_new;
   }
@@ -961,7 +979,7 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32
     const int rc = ed_cache_prepare(e, pubkeys, n_keys, n_items / 32, st, slot_of_key, tables);
     if (rc) return rc;
     if (tables) {
-      launches += e->ed.builds != before ? 2 : 0;
+      launches += e->ed.builds != before ? 2 : 0;               // table construction (two kernels per build; the first use builds twice)
       const uint64_t n_pad = (n_items + 511) / 512 * 512;
       const size_t xyz_bytes = (size_t)n_pad * 30 * sizeof(int32_t);
       const size_t slot_bytes = ((size_t)n_keys * 4 + 15) / 16 * 16;
@@ -972,7 +990,7 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32
       uint8_t* d_pre = scratch + xyz_bytes + slot_bytes;
       CU(cudaMemcpyAsync(d_slot, slot_of_key.data(), (size_t)n_keys * 4, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
       bftq::ed25519_accumulate_kernel<<<(unsigned)((n_items + bftq::kEdAccBlock - 1) / bftq::kEdAccBlock), bftq::kEdAccBlock, 0, st>>>(
-          e->ed.d_tab, e->ed.d_hdr, d_slot, n_keys, d_key_idx, d_sig, d_msg, n_items, n_pad, d_xyz, d_pre);
+          e->ed.d_tabB, e->ed.d_tab, e->ed.d_hdr, d_slot, n_keys, d_key_idx, d_sig, d_msg, n_items, n_pad, d_xyz, d_pre);
       const uint64_t fin_threads = n_pad / bftq::ed::kFxChunk;
       bftq::ed25519_finish_kernel<<<(unsigned)(fin_threads / bftq::kEdFinBlock), bftq::kEdFinBlock, 0, st>>>(d_xyz, d_pre, d_sig, n_items, n_pad, d_status);
       CU(cudaGetLastError());

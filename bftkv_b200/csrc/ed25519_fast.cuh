@@ -4,14 +4,15 @@
 //   * field products are forced inline with every limb in a register (the first version passed `fe` arrays to
 //     __noinline__ functions, i.e. through local memory), a dedicated squaring (55 instead of 100 limb products) and
 //     the interleaved 12-step carry chain curve25519 code has used since ref10;
-//   * [S]B - [k]A is at most 64 MIXED additions (7 field products each) against radix-256 window tables in affine
-//     "precomputed" form (y+x, y-x, 2dxy): table[i][j-1] = j * 256^i * P, i = 0..31, j = 1..128, 128 bytes per entry,
-//     512 KB per point.  The tables are a per-engine cache keyed by the 32 key bytes (the base point is slot 0), so a
-//     key pays its 248 doublings once per engine, not once per batch;
+//   * [S]B - [k]A is at most 48 MIXED additions (7 field products each) against window tables in affine "precomputed"
+//     form (y+x, y-x, 2dxy; 128 bytes per entry): table[i][j-1] = j * 2^(W i) * P with signed radix-2^W digits.  The base
+//     point has ONE radix-2^12 table per engine (22 windows x 2048 multiples = 5.8 MB), every key a radix-2^10 table of -A
+//     (26 windows x 512 multiples = 1.7 MB) in a per-engine cache keyed by the 32 key bytes, so a
+//     key pays its 250 doublings once per engine, not once per batch;
 //   * the final X/Z, Y/Z needs ONE inversion per eight signatures: kernel 2 (`ed25519_finish_kernel`) runs Montgomery's
 //     simultaneous inversion over eight results per thread;
 //   * k = SHA-512(R || A || M) mod L is a Barrett reduction (81 + 45 word products) instead of 512 shift-subtract steps.
-// Per verification: ~63.75 * 7 = 446 field products in kernel 1 + ~25 in kernel 2 (about 47 000 32x32->64 multiplies)
+// Per verification: ~47.9 * 7 = 335 field products in kernel 1 + ~25 in kernel 2 (about 36 000 32x32->64 multiplies)
 // instead of ~1 230 (135 000).  Semantics are unchanged (RFC 8032 §5.1.7 as Go's crypto/ed25519 / OpenSSL implement it:
 // S < L, canonical decodable A, byte compare of the encoding of [S]B - [k]A with R).
 // Everything is __host__ __device__: tests/harness/ed25519_host.cpp runs the same code on the CPU against OpenSSL,
@@ -174,11 +175,19 @@ BFTQ_HDI void fex_towords(uint32_t (&w)[8], const int32_t (&hin)[10]) {
 // ---- group ---------------------------------------------------------------------------------------------------------
 struct gea { int32_t ypx[10], ymx[10], xy2d[10], pad[2]; };       // affine (y+x, y-x, 2dxy), carried limbs; 128 bytes
 static_assert(sizeof(gea) == 128, "table entry is one 128-byte line");
-constexpr int kFxWindowBits = 8;
-constexpr int kFxWindows = 32;                                     // 256 / 8 (scalars are < 2^253)
-constexpr int kFxMultiples = 128;                                  // j = 1..128: signed digits in [-128, 127]
-constexpr int kFxEntries = kFxWindows * kFxMultiples;              // per point: 4096 entries = 512 KB
+// Window geometry for a signed radix-2^W recoding of a scalar < 2^253: W * windows >= 254, so the top digit never carries out.
+template <int W> struct FxWin {
+  static constexpr int bits = W;
+  static constexpr int windows = (253 + W) / W;                    // 8 -> 32, 10 -> 26, 12 -> 22
+  static constexpr int multiples = 1 << (W - 1);                   // j = 1 .. 2^(W-1): digits in [-2^(W-1), 2^(W-1) - 1]
+  static constexpr int entries = windows * multiples;
+};
+constexpr int kFxWB = 12;                                          // the base point: ONE table per engine, 22 x 2048 entries = 5.8 MB
+constexpr int kFxWA = 10;                                          // a key: 26 x 512 entries = 1.7 MB
+typedef FxWin<kFxWB> FxB;
+typedef FxWin<kFxWA> FxA;
 constexpr int kFxChunk = 8;                                        // table entries (and results) per simultaneous inversion
+constexpr int kFxScalarWords = 9;                                  // a scalar travels as 8 words + one zero word (a window may straddle the top)
 
 struct gex { int32_t X[10], Y[10], Z[10], T[10]; };
 
@@ -272,20 +281,25 @@ BFTQ_HDI bool sc_words_canonical(const uint32_t (&w)[8]) {
   for (int i = 7; i >= 0; i--) { if (!decided && w[i] != Lw[i]) { lt = w[i] < Lw[i]; decided = true; } }
   return lt;
 }
-// Signed radix-256 digit i of a scalar (< 2^253): d in [-128, 127], carry chained upwards through `carry`.
-BFTQ_HDI int sc_digit256(const uint32_t word, const int i, uint32_t& carry) {
-  const uint32_t d = ((word >> (8 * (i & 3))) & 255u) + carry;
-  carry = (d + 128u) >> 8;
-  return (int)d - (int)(carry << 8);
+// Signed radix-2^W digit i of a scalar (< 2^253, kFxScalarWords words, word w at sw[w * stride]): d in [-2^(W-1), 2^(W-1) - 1],
+// the carry chained upwards through `carry` (digits must be taken in ascending order).
+template <int W>
+BFTQ_HDI int sc_digit(const uint32_t* sw, const int stride, const int i, uint32_t& carry) {
+  const int bit = W * i, wi = bit >> 5, sh = bit & 31;
+  uint32_t v = sw[wi * stride] >> sh;
+  if (sh + W > 32) v |= sw[(wi + 1) * stride] << (32 - sh);
+  const uint32_t d = (v & ((1u << W) - 1u)) + carry;
+  carry = (d + (1u << (W - 1))) >> W;
+  return (int)d - (int)(carry << W);
 }
 
 // ---- table construction ----------------------------------------------------------------------------------------------
-// Step 1 (one thread per point): window bases 256^i * P, i = 0..31, as extended points with carried limbs.
-BFTQ_HD void fx_window_bases(gex* bases, const gex& P) {
+// Step 1 (one thread per point): window bases 2^(w i) * P, i = 0..nw-1, as extended points with carried limbs.
+BFTQ_HD void fx_window_bases(gex* bases, const gex& P, const int nw, const int w) {
   gex b = P;
-  for (int i = 0; i < kFxWindows; i++) {
+  for (int i = 0; i < nw; i++) {
     bases[i] = b;
-    if (i + 1 < kFxWindows) for (int t = 0; t < kFxWindowBits; t++) gex_dbl(b, b);
+    if (i + 1 < nw) for (int t = 0; t < w; t++) gex_dbl(b, b);
   }
 }
 // Step 2 (one thread per (point, window, chunk of 8 multiples)): entries (8c+1 .. 8c+8) * base in affine precomputed form,
@@ -296,7 +310,7 @@ BFTQ_HD void fx_window_chunk(gea* out, const gex& base, const int chunk) {
   const int first = kFxChunk * chunk + 1;
   gex acc = base;
   int top = 0;
-  for (int b = 7; b >= 0; b--) if ((first >> b) & 1) { top = b; break; }
+  for (int b = 12; b >= 0; b--) if ((first >> b) & 1) { top = b; break; }
   for (int b = top - 1; b >= 0; b--) { gex_dbl(acc, acc); if ((first >> b) & 1) gex_add(acc, acc, base); }
   m[0] = acc;
   for (int j = 1; j < kFxChunk; j++) gex_add(m[j], m[j - 1], base);
@@ -339,23 +353,24 @@ BFTQ_HDI void fx_load_entry(int32_t (&ypx)[10], int32_t (&ymx)[10], int32_t (&xy
   for (int i = 0; i < 10; i++) { ypx[i] = q->ypx[i]; ymx[i] = q->ymx[i]; xy2d[i] = q->xy2d[i]; }
 #endif
 }
-// [S]B - [k]A as an extended point: at most 64 mixed additions.  tabB / tabNegA: the two points' 4096-entry tables;
-// scalar word w of S is s[w * stride] (the kernel keeps the scalars in shared memory, one column per thread).
-// The caller has checked S < L and that A decodes.
+// [S]B - [k]A as an extended point: at most 22 + 26 = 48 mixed additions.  tabB: the base point's radix-2^12 table, tabNegA:
+// -A's radix-2^10 table; the scalars are kFxScalarWords words each, word w of S at s[w * stride] (the kernel keeps them in
+// shared memory, one column per thread).  The caller has checked S < L and that A decodes.
 BFTQ_HDI void fx_accumulate(gex& p, const uint32_t* s, const uint32_t* k, const int stride, const gea* tabB, const gea* tabNegA) {
   gex_identity(p);
   uint32_t cs = 0, ck = 0;
 #pragma unroll 1
-  for (int it = 0; it < 2 * kFxWindows; it++) {
-    const int which = it & 1, i = it >> 1;
-    const uint32_t word = (which ? k : s)[(i >> 2) * stride];
-    uint32_t carry = which ? ck : cs;
-    const int dig = sc_digit256(word, i, carry);
-    if (which) ck = carry; else cs = carry;
+  for (int it = 0; it < FxB::windows + FxA::windows; it++) {
+    const bool which = it >= FxB::windows;
+    const int i = which ? it - FxB::windows : it;
+    int dig;
+    const gea* q;
+    if (which) { dig = sc_digit<kFxWA>(k, stride, i, ck); q = tabNegA + i * FxA::multiples; }
+    else { dig = sc_digit<kFxWB>(s, stride, i, cs); q = tabB + i * FxB::multiples; }
     if (dig != 0) {
       const int mag = dig < 0 ? -dig : dig;
       int32_t ypx[10], ymx[10], xy2d[10];
-      fx_load_entry(ypx, ymx, xy2d, (which ? tabNegA : tabB) + (i * kFxMultiples + mag - 1));
+      fx_load_entry(ypx, ymx, xy2d, q + (mag - 1));
       gex_madd(p, ypx, ymx, xy2d, dig < 0);
     }
   }
@@ -448,15 +463,17 @@ struct EdSlotHdr { uint8_t key[32]; uint32_t ok; uint32_t pad[7]; };       // on
 static_assert(sizeof(EdSlotHdr) == 64, "slot header");
 
 // ---- table construction (runs once per key and engine) ---------------------------------------------------------------
-// Step 1: thread = one new slot.  Decodes the key (slot 0: the base point), stores -A's 32 window bases.
+// Step 1: thread = one point: decodes key number first_slot + t from its header (base_point: the one base point instead)
+// and stores the nw window bases of -A (of B).
 __global__ void __launch_bounds__(32)
-ed25519_bases_kernel(EdSlotHdr* __restrict__ hdr, const uint32_t first_slot, const uint32_t n_slots, ed::gex* __restrict__ bases) {
+ed25519_bases_kernel(EdSlotHdr* __restrict__ hdr, const uint32_t first_slot, const uint32_t n_points, ed::gex* __restrict__ bases,
+                     const int nw, const int wbits, const int base_point) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_slots) return;
-  const uint32_t slot = first_slot + t;
+  if (t >= n_points) return;
   ed::gex P;
-  if (slot == 0) { ed::gex_basepoint(P); hdr[0].ok = 1; }
+  if (base_point) ed::gex_basepoint(P);
   else {
+    const uint32_t slot = first_slot + t;
     uint8_t a[32];
     for (int i = 0; i < 32; i++) a[i] = hdr[slot].key[i];
     const bool ok = ed::gex_frombytes(P, a);
@@ -464,17 +481,17 @@ ed25519_bases_kernel(EdSlotHdr* __restrict__ hdr, const uint32_t first_slot, con
     if (!ok) ed::gex_identity(P);                              // the table is never read (every signature under the key is invalid)
     for (int i = 0; i < 10; i++) { P.X[i] = -P.X[i]; P.T[i] = -P.T[i]; }
   }
-  ed::fx_window_bases(bases + (size_t)t * ed::kFxWindows, P);
+  ed::fx_window_bases(bases + (size_t)t * nw, P, nw, wbits);
 }
-// Step 2: thread = (new slot, window, chunk of eight multiples).
+// Step 2: thread = (point, window, chunk of eight multiples); `tab` = the first point's table, `multiples` entries per window.
 __global__ void __launch_bounds__(64)
-ed25519_multiples_kernel(const ed::gex* __restrict__ bases, const uint32_t first_slot, const uint32_t n_slots, ed::gea* __restrict__ tab) {
-  constexpr int kChunks = ed::kFxMultiples / ed::kFxChunk;
+ed25519_multiples_kernel(const ed::gex* __restrict__ bases, const uint32_t n_points, const int nw, const int multiples, ed::gea* __restrict__ tab) {
+  const int chunks = multiples / ed::kFxChunk;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)n_slots * ed::kFxWindows * kChunks) return;
-  const uint32_t chunk = (uint32_t)(t % kChunks), window = (uint32_t)((t / kChunks) % ed::kFxWindows), s = (uint32_t)(t / (kChunks * ed::kFxWindows));
-  const ed::gex base = bases[(size_t)s * ed::kFxWindows + window];
-  ed::fx_window_chunk(tab + (size_t)(first_slot + s) * ed::kFxEntries + window * ed::kFxMultiples + chunk * ed::kFxChunk, base, (int)chunk);
+  if (t >= (uint64_t)n_points * nw * chunks) return;
+  const uint32_t chunk = (uint32_t)(t % chunks), window = (uint32_t)((t / chunks) % nw), s = (uint32_t)(t / ((uint64_t)chunks * nw));
+  const ed::gex base = bases[(size_t)s * nw + window];
+  ed::fx_window_chunk(tab + ((size_t)s * nw + window) * multiples + chunk * ed::kFxChunk, base, (int)chunk);
 }
 
 // ---- kernel 1: one thread per signature, [S]B - [k]A ------------------------------------------------------------------
@@ -488,11 +505,11 @@ ed25519_multiples_kernel(const ed::gex* __restrict__ bases, const uint32_t first
 #endif
 constexpr int kEdAccBlock = BFTQ_ED_ACC_BLOCK;
 __global__ void __launch_bounds__(kEdAccBlock, BFTQ_ED_ACC_MINB)
-ed25519_accumulate_kernel(const ed::gea* __restrict__ tab, const EdSlotHdr* __restrict__ hdr, const uint32_t* __restrict__ slot_of_key,
+ed25519_accumulate_kernel(const ed::gea* __restrict__ tabB, const ed::gea* __restrict__ tab, const EdSlotHdr* __restrict__ hdr, const uint32_t* __restrict__ slot_of_key,
                           const uint32_t n_keys, const uint32_t* __restrict__ key_idx, const uint8_t* __restrict__ sig,
                           const uint8_t* __restrict__ msg, const uint64_t n_items, const uint64_t n_pad,
                           int32_t* __restrict__ xyz, uint8_t* __restrict__ pre_status) {
-  __shared__ uint32_t sc[2][8][kEdAccBlock];                   // the two scalars, one column per thread
+  __shared__ uint32_t sc[2][ed::kFxScalarWords][kEdAccBlock];    // the two scalars (+ a zero word each), one column per thread
   const uint64_t item = (uint64_t)blockIdx.x * kEdAccBlock + threadIdx.x;
   if (item >= n_items) return;
   uint8_t st = 0;
@@ -538,7 +555,8 @@ ed25519_accumulate_kernel(const ed::gea* __restrict__ tab, const EdSlotHdr* __re
     ed::sc_reduce512(k, x);
 #pragma unroll
     for (int i = 0; i < 8; i++) { sc[0][i][threadIdx.x] = s[i]; sc[1][i][threadIdx.x] = k[i]; }
-    ed::fx_accumulate(p, &sc[0][0][threadIdx.x], &sc[1][0][threadIdx.x], kEdAccBlock, tab, tab + (size_t)slot * ed::kFxEntries);
+    sc[0][8][threadIdx.x] = 0u; sc[1][8][threadIdx.x] = 0u;
+    ed::fx_accumulate(p, &sc[0][0][threadIdx.x], &sc[1][0][threadIdx.x], kEdAccBlock, tabB, tab + (size_t)slot * ed::FxA::entries);
   }
 #pragma unroll
   for (int i = 0; i < 10; i++) { xyz[(size_t)i * n_pad + item] = p.X[i]; xyz[(size_t)(10 + i) * n_pad + item] = p.Y[i]; xyz[(size_t)(20 + i) * n_pad + item] = p.Z[i]; }

@@ -38,9 +38,11 @@ void ed_fex_towords_host(const uint8_t* a, const uint8_t* b, uint8_t* out) {    
   fe x, y, z; fe_frombytes(x, a); fe_frombytes(y, b); fex_mul(z, x, y); uint32_t w[8]; fex_towords(w, z); memcpy(out, w, 32);
 }
 void ed_sc_reduce512_host(const uint8_t* in64, uint8_t* out32) { uint32_t x[16], k[8]; memcpy(x, in64, 64); sc_reduce512(k, x); memcpy(out32, k, 32); }
-void ed_digits256_host(const uint8_t* s32, int32_t* out32) {
-  uint32_t w[8]; memcpy(w, s32, 32); uint32_t c = 0;
-  for (int i = 0; i < 32; i++) out32[i] = sc_digit256(w[i >> 2], i, c);
+// signed radix-2^W digits of a scalar (W = 10: 26 digits, W = 12: 22 digits)
+void ed_digits_host(const uint8_t* s32, int wbits, int32_t* out) {
+  uint32_t w[kFxScalarWords] = {0}; memcpy(w, s32, 32); uint32_t c = 0;
+  if (wbits == 10) for (int i = 0; i < FxA::windows; i++) out[i] = sc_digit<10>(w, 1, i, c);
+  else for (int i = 0; i < FxB::windows; i++) out[i] = sc_digit<12>(w, 1, i, c);
 }
 int ed_gex_roundtrip_host(const uint8_t* in, uint8_t* out) {                      // encode(3 P) via gex_dbl / gex_add / pow chain
   gex p; if (!gex_frombytes(p, in)) return 0;
@@ -52,18 +54,21 @@ int ed_gex_roundtrip_host(const uint8_t* in, uint8_t* out) {                    
   return 1;
 }
 // Table of one point exactly as the two table kernels build it (bases, then chunks of eight multiples).
-static void fx_build_table(std::vector<gea>& tab, const gex& P) {
-  tab.resize(kFxEntries);
-  std::vector<gex> bases(kFxWindows);
-  fx_window_bases(bases.data(), P);
-  for (int w = 0; w < kFxWindows; w++)
-    for (int c = 0; c < kFxMultiples / kFxChunk; c++) fx_window_chunk(tab.data() + w * kFxMultiples + c * kFxChunk, bases[w], c);
+static void fx_build_table(std::vector<gea>& tab, const gex& P, int nw, int wbits) {
+  const int multiples = 1 << (wbits - 1);
+  tab.resize((size_t)nw * multiples);
+  std::vector<gex> bases(nw);
+  fx_window_bases(bases.data(), P, nw, wbits);
+  for (int w = 0; w < nw; w++)
+    for (int c = 0; c < multiples / kFxChunk; c++) fx_window_chunk(tab.data() + (size_t)w * multiples + c * kFxChunk, bases[w], c);
 }
-// table entry j of window w as the affine point's encoding (checked against big-integer arithmetic by the test)
-int ed_fx_table_entry_host(const uint8_t* pk, int window, int j, uint8_t* out_ypx, uint8_t* out_ymx, uint8_t* out_xy2d) {
-  static std::vector<gea> tab; static uint8_t last[32]; static bool have = false;
-  if (!have || memcmp(last, pk, 32) != 0) { gex A; if (!gex_frombytes(A, pk)) return 0; fx_build_table(tab, A); memcpy(last, pk, 32); have = true; }
-  const gea& e = tab[window * kFxMultiples + j - 1];
+// table entry j of window w of a key's radix-2^10 table (base = 1: the base point's radix-2^12 table) as the affine
+// point's encoding (checked against big-integer arithmetic by the test)
+int ed_fx_table_entry_host(const uint8_t* pk, int base, int window, int j, uint8_t* out_ypx, uint8_t* out_ymx, uint8_t* out_xy2d) {
+  static std::vector<gea> tab, tabB; static uint8_t last[32]; static bool have = false;
+  if (base) { if (tabB.empty()) { gex B; gex_basepoint(B); fx_build_table(tabB, B, FxB::windows, kFxWB); } }
+  else if (!have || memcmp(last, pk, 32) != 0) { gex A; if (!gex_frombytes(A, pk)) return 0; fx_build_table(tab, A, FxA::windows, kFxWA); memcpy(last, pk, 32); have = true; }
+  const gea& e = base ? tabB[(size_t)window * FxB::multiples + j - 1] : tab[(size_t)window * FxA::multiples + j - 1];
   fe_tobytes(out_ypx, e.ypx); fe_tobytes(out_ymx, e.ymx); fe_tobytes(out_xy2d, e.xy2d);
   for (int i = 0; i < 10; i++) {                    // entries must be carried: safe as fex_mul's second operand
     const int lim = (i & 1) ? (1 << 24) + (1 << 18) : (1 << 25) + (1 << 19);
@@ -76,33 +81,34 @@ int ed_verify_fast_host(const uint8_t* sig, const uint8_t* pk, const uint8_t* k6
   static std::vector<gea> tabB, tabA;
   static uint8_t last_pk[32];
   static int last_ok = -1;
-  if (tabB.empty()) { gex B; gex_basepoint(B); fx_build_table(tabB, B); }
+  if (tabB.empty()) { gex B; gex_basepoint(B); fx_build_table(tabB, B, FxB::windows, kFxWB); }
   if (last_ok < 0 || memcmp(last_pk, pk, 32) != 0) {
     gex A;
     last_ok = gex_frombytes(A, pk) ? 1 : 0;
     memcpy(last_pk, pk, 32);
-    if (last_ok) { for (int i = 0; i < 10; i++) { A.X[i] = -A.X[i]; A.T[i] = -A.T[i]; } fx_build_table(tabA, A); }
+    if (last_ok) { for (int i = 0; i < 10; i++) { A.X[i] = -A.X[i]; A.T[i] = -A.T[i]; } fx_build_table(tabA, A, FxA::windows, kFxWA); }
   }
   if (!last_ok) return 0;
-  uint32_t x[16], k[8], s[8], r[8];
+  uint32_t x[16], k[8], s[8], r[8], s9[kFxScalarWords] = {0}, k9[kFxScalarWords] = {0};
   memcpy(x, k64, 64); sc_reduce512(k, x);
   memcpy(r, sig, 32); memcpy(s, sig + 32, 32);
   if (!sc_words_canonical(s)) return 0;
+  memcpy(s9, s, 32); memcpy(k9, k, 32);
   gex p;
-  fx_accumulate(p, s, k, 1, tabB.data(), tabA.data());
+  fx_accumulate(p, s9, k9, 1, tabB.data(), tabA.data());
   fe zi; fex_pow_chain(zi, p.Z, true);
   return fx_encodes_to(p.X, p.Y, zi, r) ? 1 : 0;
 }
 // max |limb| seen on the accumulator after a verification's additions (bounds check of the lazy-carry discipline)
 int ed_fast_limb_bound_host(const uint8_t* sig, const uint8_t* pk, const uint8_t* k64) {
   static std::vector<gea> tabB, tabA;
-  if (tabB.empty()) { gex B; gex_basepoint(B); fx_build_table(tabB, B); }
+  if (tabB.empty()) { gex B; gex_basepoint(B); fx_build_table(tabB, B, FxB::windows, kFxWB); }
   gex A; if (!gex_frombytes(A, pk)) return -1;
   for (int i = 0; i < 10; i++) { A.X[i] = -A.X[i]; A.T[i] = -A.T[i]; }
-  fx_build_table(tabA, A);
-  uint32_t x[16], k[8], s[8];
-  memcpy(x, k64, 64); sc_reduce512(k, x); memcpy(s, sig + 32, 32);
-  gex p; fx_accumulate(p, s, k, 1, tabB.data(), tabA.data());
+  fx_build_table(tabA, A, FxA::windows, kFxWA);
+  uint32_t x[16], k[8], s9[kFxScalarWords] = {0}, k9[kFxScalarWords] = {0};
+  memcpy(x, k64, 64); sc_reduce512(k, x); memcpy(s9, sig + 32, 32); memcpy(k9, k, 32);
+  gex p; fx_accumulate(p, s9, k9, 1, tabB.data(), tabA.data());
   int m = 0;
   for (int i = 0; i < 10; i++) for (const int32_t* c : {p.X, p.Y, p.Z, p.T}) { const int v = c[i] < 0 ? -c[i] : c[i]; if (v > m) m = v; }
   return m;

@@ -185,24 +185,30 @@ def test_fast_field_scalar_and_tables(host):
         host.ed_sc_reduce512_host(v, out)
         assert int.from_bytes(out.raw[:32], "little") == int.from_bytes(v, "little") % L, v.hex()
     dg = (ctypes.c_int32 * 32)()
-    for _ in range(500):                                   # sum d_i 256^i == s, d_i in [-128, 127]
+    for _ in range(500):                                   # sum d_i 2^(W i) == s, d_i in [-2^(W-1), 2^(W-1) - 1], for both window widths
         sc = rng.choice([rng.randrange(L), L - 1, 0, 1, 2 ** 252, int("80" * 31, 16), int("7f" * 31, 16), int("ff" * 31, 16), 2 ** 252 + 2 ** 251,
-                         int("1f" + "ff" * 31, 16)])
-        host.ed_digits256_host(sc.to_bytes(32, "little"), dg)
-        assert all(-128 <= v <= 127 for v in dg) and sum(v * 256 ** i for i, v in enumerate(dg)) == sc
+                         int("1f" + "ff" * 31, 16), int("0f" + "ff" * 31, 16), (1 << 250) - 1, 511 * sum(1 << (10 * i) for i in range(25)),
+                         512 * sum(1 << (10 * i) for i in range(25)), 2048 * sum(1 << (12 * i) for i in range(21))])
+        for wbits, nw in ((10, 26), (12, 22)):
+            host.ed_digits_host(sc.to_bytes(32, "little"), wbits, dg)
+            d = list(dg)[:nw]
+            assert all(-(1 << (wbits - 1)) <= v < (1 << (wbits - 1)) for v in d) and sum(v << (wbits * i) for i, v in enumerate(d)) == sc, (hex(sc), wbits)
     # 3 P through gex_dbl / gex_add / the inversion chain
     sks, pks, *_ = make_sigs(1, 3, 21)
     for pk in pks:
         assert host.ed_gex_roundtrip_host(pk, out) == 1
         x3, y3 = _edwards_mul(3, _decode_point(pk))
         assert int.from_bytes(out.raw[:32], "little") == y3 | ((x3 & 1) << 255)
-    # table entries of a key: j * 256^w * A
+    # table entries: j * 2^(10 w) * A for a key (26 windows x 512 multiples), j * 2^(12 w) * B for the base point (22 x 2048)
     A = _decode_point(pks[0])
+    Bpt = _decode_point((4 * pow(5, -1, P) % P).to_bytes(32, "little"))
     e1, e2, e3 = (ctypes.create_string_buffer(32) for _ in range(3))
-    for w, j in [(0, 1), (0, 2), (0, 8), (0, 9), (0, 128), (1, 1), (1, 77), (5, 121), (17, 64), (31, 1), (31, 31), (31, 128)] + \
-                [(rng.randrange(32), rng.randrange(1, 129)) for _ in range(20)]:
-        assert host.ed_fx_table_entry_host(pks[0], w, j, e1, e2, e3) == 1, "entry not carried"
-        x, y = _edwards_mul(j * 256 ** w, A)
+    cases = [(0, 0, 1), (0, 0, 2), (0, 0, 8), (0, 0, 9), (0, 0, 512), (0, 1, 1), (0, 1, 77), (0, 5, 505), (0, 17, 64), (0, 25, 1), (0, 25, 8), (0, 25, 512),
+             (1, 0, 1), (1, 0, 2048), (1, 3, 2041), (1, 21, 1), (1, 21, 2), (1, 10, 1025)] + \
+            [(0, rng.randrange(26), rng.randrange(1, 513)) for _ in range(15)] + [(1, rng.randrange(22), rng.randrange(1, 2049)) for _ in range(15)]
+    for base, w, j in cases:
+        assert host.ed_fx_table_entry_host(pks[0], base, w, j, e1, e2, e3) == 1, "entry not carried"
+        x, y = _edwards_mul(j << ((12 if base else 10) * w), Bpt if base else A)
         assert int.from_bytes(e1.raw, "little") == (y + x) % P and int.from_bytes(e2.raw, "little") == (y - x) % P
         assert int.from_bytes(e3.raw, "little") == 2 * D * x * y % P
 
