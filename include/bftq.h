@@ -160,9 +160,10 @@ int bftq_rsa_verify_batch_dev_k(bftq_engine* e, uint32_t key_bytes, const uint32
  * sig: n_items x 64 (R || S), msg: n_items x 32.  out_status: BFTQ_ST_OK / _BAD_SIGNATURE /
  * _UNKNOWN_SIGNER.  Rejects S >= L and non-canonical / off-curve A like Go's crypto/ed25519.
  * Keys are metadata, like the RSA key table: `pubkeys` is HOST memory in both forms (the _dev form takes the bulk arrays
- * key_idx / sig / msg / status in device memory).  Batches run against radix-256 window tables that the engine caches
- * per key (512 KB each, built on first sight of the 32 key bytes, bounded by BFTQ_ED25519_CACHE_SLOTS = 256 slots); a
- * batch that would bring more than one new key per 32 signatures uses the table-free double-and-add kernel. */
+ * key_idx / sig / msg / status in device memory).  Batches run against window tables that the engine caches: one for
+ * the base point (5.8 MB) and one per key (1.7 MB each, built on first sight of the 32 key bytes, bounded by
+ * BFTQ_ED25519_CACHE_SLOTS = 256 slots); a batch that would bring more than one new key per 32 signatures uses the
+ * table-free double-and-add kernel. */
 int bftq_ed25519_verify_batch(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* key_idx,
                               const uint8_t* sig, const uint8_t* msg, uint64_t n_items, uint8_t* out_status);
 int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, const uint32_t* d_key_idx,
