@@ -179,7 +179,8 @@ struct EdCache {
   bftq::ed::gea* d_tabB = nullptr;               // FxB::entries entries (the base point)
   bftq::EdSlotHdr* d_hdr = nullptr;
   uint32_t cap_slots = 0, used = 0;
-  uint64_t builds = 0;                           // slots built so far
+  uint64_t builds = 0;                           // tables built so far
+  uint64_t resets = 0;                           // times a full cache was emptied for a batch that pays for its tables
   std::map<std::string, uint32_t> slot_of;       // 32 key bytes -> slot
   std::vector<cudaEvent_t> pending;              // builds that may still be running
 };
@@ -934,23 +935,44 @@ int ed_cache_prepare(bftq_engine* e, const uint8_t* pubkeys, uint32_t n_keys, ui
     if (rc) return rc;
     c.builds += 1;
   }
-  const uint32_t first = c.used;
   const uint32_t n_new = (uint32_t)fresh.size();
-  if ((uint64_t)first + n_new > c.cap_slots) return BFTQ_OK;   // does not fit: caller takes the table-free kernel
+  if ((uint64_t)c.used + n_new > c.cap_slots) {
+    // Full.  Slots are never evicted one by one (readers of any stream may be using them); a batch that would clearly pay
+    // for its tables (128 signatures per new key) and fits an empty cache empties it instead — after the device has drained.
+    // Anything smaller takes the table-free kernel, so junk keys cannot make the engine thrash.
+    if (n_new > c.cap_slots || max_new < 4ull * n_new) return BFTQ_OK;
+    CU(cudaDeviceSynchronize());
+    for (cudaEvent_t ev : c.pending) cudaEventDestroy(ev);
+    c.pending.clear();
+    c.slot_of.clear();
+    c.used = 0;
+    c.resets++;
+    // every key of the call is new now: rebuild the list in first-seen order
+    fresh.clear(); fresh_idx.clear();
+    for (uint32_t i = 0; i < n_keys; i++) {
+      std::string kb((const char*)pubkeys + (size_t)i * 32, 32);
+      auto f = fresh_idx.find(kb);
+      if (f == fresh_idx.end()) { f = fresh_idx.emplace(kb, (uint32_t)fresh.size()).first; fresh.push_back(kb); }
+      slot_of_key[i] = 0x80000000u | f->second;
+    }
+    if (fresh.size() > c.cap_slots || fresh.size() > max_new) { fits = false; return BFTQ_OK; }
+  }
+  const uint32_t first = c.used;
   // earlier builds on other streams must be complete before this stream reads their tables
   for (size_t i = 0; i < c.pending.size();) {
     if (cudaEventQuery(c.pending[i]) == cudaSuccess) { cudaEventDestroy(c.pending[i]); c.pending[i] = c.pending.back(); c.pending.pop_back(); }
     else { cudaGetLastError(); CU(cudaStreamWaitEvent(st, c.pending[i], 0)); i++; }
   }
-  if (n_new) {
+  if (!fresh.empty()) {
+    const uint32_t n_build = (uint32_t)fresh.size();
     std::vector<bftq::EdSlotHdr> h(fresh.size());
     for (size_t i = 0; i < fresh.size(); i++) { memset(&h[i], 0, sizeof(h[i])); memcpy(h[i].key, fresh[i].data(), 32); }
     CU(cudaMemcpyAsync(c.d_hdr + first, h.data(), h.size() * sizeof(bftq::EdSlotHdr), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
-    const int rc = ed_build_tables(c, st, first, n_new, false);
+    const int rc = ed_build_tables(c, st, first, n_build, false);
     if (rc) return rc;
     for (size_t i = 0; i < fresh.size(); i++) c.slot_of.emplace(fresh[i], first + (uint32_t)i);
-    c.used = first + n_new;
-    c.builds += n_new;
+    c.used = first + n_build;
+    c.builds += n_build;
   }
   for (uint32_t i = 0; i < n_keys; i++) if (slot_of_key[i] & 0x80000000u) slot_of_key[i] = c.slot_of[fresh[slot_of_key[i] & 0x7fffffffu]];
   fits = true;
@@ -965,8 +987,8 @@ int bftq_ed25519_verify_batch_dev(bftq_engine* e, const uint8_t* pubkeys, uint32
   if (n_items == 0) return BFTQ_OK;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  // Signatures run against the cached window tables: at most 64 mixed additions each and no doubling.  A table costs
-  // about 400 such verifications' worth of work once per key and engine (about 50 table-free ones), so a batch may
+  // Signatures run against the cached window tables: at most 48 mixed additions each and no doubling.  A table costs
+  // about 1 000 such verifications' worth of work once per key and engine (about 100 table-free ones), so a batch may
   // bring one NEW key per 32 signatures; keys that are cached already cost nothing, whatever the batch size.  Batches
   // with more new keys than that (every signature under its own key, say) take the table-free double-and-add kernel.
   static const bool no_tables = [] { const char* v = getenv("BFTQ_ED25519_TABLES"); return v && atoi(v) == 0; }();

@@ -151,7 +151,7 @@ def _decode_point(b):
 
 def test_fast_field_scalar_and_tables(host):
     """ed25519_fast.cuh on the host: inlined product / squaring (carried and uncarried operands at the documented bounds),
-    the addition-chain powers, canonical words, the Barrett reduction mod L, the signed radix-256 recoding, and window-table
+    the addition-chain powers, canonical words, the Barrett reduction mod L, the signed radix-2^10 / 2^12 recodings, and window-table
     entries against big-integer Edwards arithmetic (affine y+x, y-x, 2dxy; limbs carried)."""
     rng = random.Random(2)
     out = ctypes.create_string_buffer(64)
@@ -324,3 +324,33 @@ def test_ed25519_gpu_batch(engine):
     expb = np.array([0 if openssl_ok(sks[kb[i]], allbad[i].tobytes(), msg[i].tobytes()) else 1 for i in range(2304)], np.uint8)
     gotb = engine.ed25519_verify_batch(pk_arr, kb, allbad, msg[:2304])
     assert np.array_equal(gotb, expb) and (gotb == 1).sum() > 2290
+
+
+@pytest.mark.gpu
+def test_ed25519_table_cache_full_gpu():
+    """A table cache of four slots: a second key set that pays for its tables (>= 128 signatures per new key) empties the
+    full cache and is verified against fresh tables; a small batch under yet other keys takes the table-free kernel; the
+    first key set comes back afterwards.  Every status against OpenSSL."""
+    from bftkv_b200 import Engine
+    old = os.environ.get("BFTQ_ED25519_CACHE_SLOTS")
+    os.environ["BFTQ_ED25519_CACHE_SLOTS"] = "4"
+    eng = Engine(0)
+    try:
+        def batch(n, n_keys, seed):
+            sks, pks, kidx, msg, sig, rng = make_sigs(n, n_keys, seed)
+            expect = np.zeros(n, np.uint8)
+            for i in range(0, n, 7):
+                sig[i, rng.randrange(64)] ^= np.uint8(1 << rng.randrange(8))
+                expect[i] = 0 if openssl_ok(sks[kidx[i]], sig[i].tobytes(), msg[i].tobytes()) else 1
+            return np.frombuffer(b"".join(pks), np.uint8).reshape(n_keys, 32).copy(), kidx, sig, msg, expect
+        a = batch(600, 3, 301)
+        b = batch(600, 3, 302)
+        c = batch(100, 3, 303)
+        for pk, kidx, sig, msg, expect in (a, b, c, a, b):
+            assert np.array_equal(eng.ed25519_verify_batch(pk, kidx, sig, msg), expect)
+    finally:
+        eng.close()
+        if old is None:
+            os.environ.pop("BFTQ_ED25519_CACHE_SLOTS", None)
+        else:
+            os.environ["BFTQ_ED25519_CACHE_SLOTS"] = old
